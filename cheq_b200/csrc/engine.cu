@@ -1,0 +1,1287 @@
+// Host orchestration and C ABI of the B200 QEq engine (include/cheq_b200.h).
+//
+// One call = QEqSolver::solve / solve_in_field after element lookup
+// (/root/reference/src/solver/implementation.rs:174-188, 239-266):
+//   typing + ordering (host, O(N)) -> pair tables (host, per distinct element pair, cached)
+//   -> v_ext kernel (:369-447) -> matrix assembly kernel (:454-554)
+//   -> blocked Cholesky of the non-hydrogen block and the hydrogen Schur complement, once
+//   -> SCF loop (:273-345): only the hydrogen block is refactorised per iteration; damping, clamp and
+//      convergence logic run on the device, the host reads back one small record per iteration.
+// There is no CPU fallback: every numerical step is a kernel of kernels_*.cu.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "../../include/cheq_b200.h"
+#include "device_types.h"
+#include "kernels.h"
+#include "sto_tables.h"
+
+using namespace cheq;
+
+namespace {
+
+struct DeviceBuffer {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 16;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    template <class T>
+    T* as() const { return (T*)p; }
+};
+
+using Clock = std::chrono::steady_clock;
+double ms_since(Clock::time_point t0) {
+    return std::chrono::duration<double, std::milli>(Clock::now() - t0).count();
+}
+
+struct TableKey {
+    int n1, n2;
+    uint64_t z1, z2;
+    bool operator<(const TableKey& o) const { return std::tie(n1, n2, z1, z2) < std::tie(o.n1, o.n2, o.z1, o.z2); }
+};
+uint64_t bits(double x) {
+    uint64_t u;
+    std::memcpy(&u, &x, 8);
+    return u;
+}
+
+struct ElementType {
+    uint8_t n;
+    double radius;
+};
+
+// Internal ordering of one topology.
+struct Layout {
+    long n = 0;
+    int nx = 0, nh = 0, nxp = 0, nhp = 0, NP = 0, MT = 0;
+    long ld = 0;
+    bool scf = false;
+    std::vector<int> perm;            // NP, internal -> input, -1 padding
+    std::vector<uint8_t> type;        // NP
+    std::vector<ElementType> types;   // distinct (n, radius), atoms first, then external charges
+};
+
+int round_up_tile(int v) { return ((v + kTile - 1) / kTile) * kTile; }
+
+}  // namespace
+
+struct cheq_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex mu;
+    std::string err;
+    std::map<TableKey, StoPairTable> sto_cache;
+    cheq_stats stats{};
+    // device workspace (grow-only)
+    DeviceBuffer in_xyz, in_chi, in_hard, in_radius, in_nq, perm, type, x, y, z, diag, chi, hard, vext, A, S0,
+        Linv, v, q, scratch, counters, state, active, blob, pc_xyz, pc_q, pc_type, out_q, misc0, misc1, misc2,
+        lu_f, lu_piv;
+    ScfState* h_state = nullptr;   // pinned
+    int* h_active = nullptr;       // pinned
+    size_t h_state_cap = 0;
+    cudaEvent_t ev[8]{};
+    uint64_t launches = 0;
+};
+
+namespace {
+
+#define CU(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t e__ = (call);                                                        \
+        if (e__ != cudaSuccess) {                                                        \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);              \
+            cudaGetLastError();                                                          \
+            return (e__ == cudaErrorMemoryAllocation) ? CHEQ_ERR_OUT_OF_MEMORY : CHEQ_ERR_CUDA; \
+        }                                                                                \
+    } while (0)
+
+#define LAUNCH(call)      \
+    do {                  \
+        CU(call);         \
+        ctx->launches++;  \
+    } while (0)
+
+int fail(cheq_ctx* ctx, int code, const std::string& msg) {
+    ctx->err = msg;
+    return code;
+}
+
+double slater_exponent(unsigned n, double r_cov_bohr, double lambda) {
+    // sto.rs:43-48 / gto.rs:47-52
+    if (r_cov_bohr < kDistanceThresholdBohr) return 0.0;
+    return lambda * (2.0 * (double)n + 1.0) / (2.0 * r_cov_bohr);
+}
+double gto_fitting_coefficient(unsigned n) {
+    // gto.rs:69-78
+    switch (n) {
+        case 1: return 0.270917;
+        case 2: return 0.098800;
+        case 3: return 0.055600;
+        case 4: return 0.039100;
+        case 5: return 0.029600;
+        default: return 0.27 * std::pow((double)n, -1.35);
+    }
+}
+double gto_gaussian_exponent(unsigned n, double zeta) {
+    // gto.rs:56-62
+    if (n == 0) return 0.0;
+    return gto_fitting_coefficient(n) * zeta * zeta / (double)n;
+}
+
+int find_or_add_type(std::vector<ElementType>& types, std::map<std::pair<uint8_t, uint64_t>, int>& index,
+                     uint8_t n, double radius) {
+    auto key = std::make_pair(n, bits(radius));
+    auto it = index.find(key);
+    if (it != index.end()) return it->second;
+    int id = (int)types.size();
+    types.push_back({n, radius});
+    index.emplace(key, id);
+    return id;
+}
+
+// Typing and ordering: non-hydrogen block first, then the n == 1 block (implementation.rs:475-477), each
+// sorted by element type so that warps of the assembly kernel see one pair type.
+int make_layout(cheq_ctx* ctx, long n, const double* radius, const uint8_t* nq, bool hydrogen_scf,
+                const double* pc_radius, const uint8_t* pc_n, long m, Layout& L, std::vector<int>& pc_type) {
+    L.n = n;
+    std::map<std::pair<uint8_t, uint64_t>, int> index;
+    std::vector<int> atom_type(n);
+    for (long i = 0; i < n; ++i) atom_type[i] = find_or_add_type(L.types, index, nq[i], radius[i]);
+    pc_type.resize(m);
+    for (long k = 0; k < m; ++k) pc_type[k] = find_or_add_type(L.types, index, pc_n[k], pc_radius[k]);
+    if (L.types.size() >= kPadType) return fail(ctx, CHEQ_ERR_INVALID_ARGUMENT, "more than 254 distinct element types");
+    bool any_h = false;
+    for (long i = 0; i < n; ++i) any_h |= (nq[i] == 1);
+    L.scf = hydrogen_scf && any_h;   // implementation.rs:279-280
+    std::vector<int> xs, hs;
+    xs.reserve(n);
+    for (long i = 0; i < n; ++i) {
+        if (L.scf && nq[i] == 1) hs.push_back((int)i);
+        else xs.push_back((int)i);
+    }
+    auto by_type = [&](int a, int b) { return atom_type[a] != atom_type[b] ? atom_type[a] < atom_type[b] : a < b; };
+    std::sort(xs.begin(), xs.end(), by_type);
+    std::sort(hs.begin(), hs.end(), by_type);
+    L.nx = (int)xs.size();
+    L.nh = (int)hs.size();
+    L.nxp = round_up_tile(L.nx);
+    L.nhp = round_up_tile(L.nh);
+    L.NP = L.nxp + L.nhp;
+    L.MT = L.NP + kRhsRows;
+    L.ld = L.MT;
+    L.perm.assign(L.NP, -1);
+    L.type.assign(L.NP, kPadType);
+    for (int i = 0; i < L.nx; ++i) {
+        L.perm[i] = xs[i];
+        L.type[i] = (uint8_t)atom_type[xs[i]];
+    }
+    for (int i = 0; i < L.nh; ++i) {
+        L.perm[L.nxp + i] = hs[i];
+        L.type[L.nxp + i] = (uint8_t)atom_type[hs[i]];
+    }
+    return CHEQ_OK;
+}
+
+struct PackedTables {
+    std::vector<char> blob;
+    PairTableView view{};   // pointers are OFFSETS into blob until rebased
+    int pair_types = 0;
+};
+
+// Builds the pair tables for all type pairs, in Angstrom units.
+int pack_tables(cheq_ctx* ctx, const std::vector<ElementType>& types, double lambda, int basis, PackedTables& out) {
+    const int T = (int)types.size();
+    std::vector<double> rcut2(T * T, 0.0), rzero2(T * T, 0.0), j0(T * T, 0.0), beta(T * T, 0.0), term_c, coef;
+    std::vector<int> term_begin(T * T, 0), term_count(T * T, 0), coef_begin, coef_count;
+    std::vector<double> zeta(T);
+    for (int i = 0; i < T; ++i) zeta[i] = slater_exponent(types[i].n, types[i].radius / kBohrToAngstrom, lambda);
+    const double B = kBohrToAngstrom;
+    for (int i = 0; i < T; ++i)
+        for (int j = i; j < T; ++j) {
+            const int p = i * T + j, pt = j * T + i;
+            if (basis == CHEQ_BASIS_GTO) {
+                // gto.rs:36-42, 82-90
+                const double a1 = gto_gaussian_exponent(types[i].n, zeta[i]);
+                const double a2 = gto_gaussian_exponent(types[j].n, zeta[j]);
+                const double b = std::sqrt(2.0 * a1 * a2 / (a1 + a2));
+                beta[p] = beta[pt] = b / B;
+                // `r > DISTANCE_THRESHOLD_BOHR` else 2 beta / sqrt(pi): r2 < rzero2 takes the else branch
+                const double rz = kDistanceThresholdBohr * B;
+                rzero2[p] = rzero2[pt] = std::nextafter(rz * rz, 1.0);
+                j0[p] = j0[pt] = 2.0 * b / std::sqrt(M_PI) * kHartreeToEv;
+                continue;
+            }
+            TableKey key{types[i].n, types[j].n, bits(zeta[i]), bits(zeta[j])};
+            auto it = ctx->sto_cache.find(key);
+            if (it == ctx->sto_cache.end())
+                it = ctx->sto_cache.emplace(key, build_sto_pair_table(types[i].n, zeta[i], types[j].n, zeta[j])).first;
+            const StoPairTable& tab = it->second;
+            if (tab.kind == STO_KIND_INVALID) {
+                // zeta == 0 or n == 0: undefined in the reference's dependency; propagate NaN
+                rzero2[p] = rzero2[pt] = 1e300;
+                j0[p] = j0[pt] = std::nan("");
+                continue;
+            }
+            rcut2[p] = rcut2[pt] = (tab.r_cut * B) * (tab.r_cut * B);
+            rzero2[p] = rzero2[pt] = (tab.r_zero * B) * (tab.r_zero * B);
+            j0[p] = j0[pt] = tab.j0 * kHartreeToEv;
+            term_begin[p] = term_begin[pt] = (int)term_c.size();
+            term_count[p] = term_count[pt] = (int)tab.terms.size();
+            for (const StoTerm& t : tab.terms) {
+                term_c.push_back(t.c / B);
+                coef_begin.push_back((int)coef.size());
+                coef_count.push_back((int)t.coef.size());
+                double scale = 1.0;
+                for (double c : t.coef) {
+                    coef.push_back(c * scale);
+                    scale /= B;
+                }
+            }
+            out.pair_types++;
+        }
+    if (basis == CHEQ_BASIS_GTO) out.pair_types = T * (T + 1) / 2;
+    // layout: doubles, then ints
+    const size_t nd = 4 * (size_t)T * T + term_c.size() + coef.size();
+    const size_t ni = 2 * (size_t)T * T + coef_begin.size() + coef_count.size();
+    size_t bytes = nd * 8 + ni * 4;
+    bytes = (bytes + 15) / 16 * 16;
+    out.blob.assign(bytes, 0);
+    char* base = out.blob.data();
+    size_t off = 0;
+    auto put_d = [&](const std::vector<double>& v) {
+        const double* p = (const double*)(uintptr_t)off;
+        if (!v.empty()) std::memcpy(base + off, v.data(), v.size() * 8);
+        off += v.size() * 8;
+        return p;
+    };
+    auto put_i = [&](const std::vector<int>& v) {
+        const int* p = (const int*)(uintptr_t)off;
+        if (!v.empty()) std::memcpy(base + off, v.data(), v.size() * 4);
+        off += v.size() * 4;
+        return p;
+    };
+    out.view.num_types = T;
+    out.view.basis = basis;
+    out.view.rcut2 = put_d(rcut2);
+    out.view.rzero2 = put_d(rzero2);
+    out.view.j0 = put_d(j0);
+    out.view.beta = put_d(beta);
+    out.view.term_c = put_d(term_c);
+    out.view.coef = put_d(coef);
+    out.view.term_begin = put_i(term_begin);
+    out.view.term_count = put_i(term_count);
+    out.view.coef_begin = put_i(coef_begin);
+    out.view.coef_count = put_i(coef_count);
+    return CHEQ_OK;
+}
+
+PairTableView rebase_view(PairTableView v, const char* base) {
+    auto mv = [&](const void* p) { return (const void*)(base + (uintptr_t)p); };
+    v.rcut2 = (const double*)mv(v.rcut2);
+    v.rzero2 = (const double*)mv(v.rzero2);
+    v.j0 = (const double*)mv(v.j0);
+    v.beta = (const double*)mv(v.beta);
+    v.term_begin = (const int*)mv(v.term_begin);
+    v.term_count = (const int*)mv(v.term_count);
+    v.term_c = (const double*)mv(v.term_c);
+    v.coef_begin = (const int*)mv(v.coef_begin);
+    v.coef_count = (const int*)mv(v.coef_count);
+    v.coef = (const double*)mv(v.coef);
+    return v;
+}
+
+int upload_tables(cheq_ctx* ctx, const PackedTables& pk, PairTableView& dev_view) {
+    CU(ctx->blob.ensure(pk.blob.size()));
+    CU(cudaMemcpyAsync(ctx->blob.p, pk.blob.data(), pk.blob.size(), cudaMemcpyHostToDevice, ctx->stream));
+    dev_view = rebase_view(pk.view, ctx->blob.as<char>());
+    return CHEQ_OK;
+}
+
+// ---- factorisation driver ------------------------------------------------------------------------------------
+struct Dense {
+    cheq_ctx* ctx;
+    double* A;
+    long ld, strideA;
+    double* Linv;
+    long strideLinv;
+    int MT;
+    ScfState* state;
+    int batch;
+    double flops = 0.0;
+};
+
+// Recursive tall-panel Cholesky of columns [j0, j0 + n) with all rows down to MT (the rows below the panel are
+// overwritten by A L^-T, i.e. the triangular solve is part of every leaf).
+int factor_panel(Dense& D, int j0, int n) {
+    cheq_ctx* ctx = D.ctx;
+    if (n <= 0) return CHEQ_OK;
+    if (n == kTile) {
+        double* Ajj = D.A + (long)j0 + (long)j0 * D.ld;
+        double* Lk = D.Linv + (long)(j0 / kTile) * kTile * kTile;
+        LAUNCH(launch_potrf_tile(Ajj, D.ld, D.strideA, Lk, D.strideLinv, D.state, D.batch, ctx->stream));
+        const int mt = (D.MT - j0 - kTile) / kTile;
+        if (mt > 0) {
+            GemmArgs g{};
+            g.A = Ajj + kTile;
+            g.lda = D.ld;
+            g.strideA = D.strideA;
+            g.B = Lk;
+            g.ldb = kTile;
+            g.strideB = D.strideLinv;
+            g.C = Ajj + kTile;
+            g.ldc = D.ld;
+            g.strideC = D.strideA;
+            g.K = kTile;
+            g.lower = 0;
+            g.subtract = 0;
+            g.state = D.state;
+            LAUNCH(launch_gemm_nt(g, mt, 1, D.batch, ctx->stream));
+        }
+        const double m = (double)(D.MT - j0 - kTile);
+        D.flops += (double)kTile * kTile * kTile / 3.0 + m * kTile * kTile;
+        return CHEQ_OK;
+    }
+    const int n1 = ((n / kTile) / 2) * kTile;
+    int rc = factor_panel(D, j0, n1);
+    if (rc) return rc;
+    {
+        const int r0 = j0 + n1;
+        GemmArgs g{};
+        g.A = D.A + (long)r0 + (long)j0 * D.ld;
+        g.lda = D.ld;
+        g.strideA = D.strideA;
+        g.B = g.A;
+        g.ldb = D.ld;
+        g.strideB = D.strideA;
+        g.C = D.A + (long)r0 + (long)r0 * D.ld;
+        g.ldc = D.ld;
+        g.strideC = D.strideA;
+        g.K = n1;
+        g.lower = 1;
+        g.subtract = 1;
+        g.state = D.state;
+        const int mt = (D.MT - r0) / kTile, nt = (n - n1) / kTile;
+        LAUNCH(launch_gemm_nt(g, mt, nt, D.batch, ctx->stream));
+        const double w = (double)(n - n1), m = (double)(D.MT - r0);
+        D.flops += (double)n1 * (w * w + 2.0 * (m - w) * w);   // syrk on the square part + gemm below it
+    }
+    return factor_panel(D, j0 + n1, n - n1);
+}
+
+// Schur update of the trailing block by an already factored leading block [0, k): C[k:MT, k:NP] -= W W^T.
+int schur_update(Dense& D, int k, int ncols) {
+    cheq_ctx* ctx = D.ctx;
+    if (k <= 0 || ncols <= 0) return CHEQ_OK;
+    GemmArgs g{};
+    g.A = D.A + (long)k;
+    g.lda = D.ld;
+    g.strideA = D.strideA;
+    g.B = g.A;
+    g.ldb = D.ld;
+    g.strideB = D.strideA;
+    g.C = D.A + (long)k + (long)k * D.ld;
+    g.ldc = D.ld;
+    g.strideC = D.strideA;
+    g.K = k;
+    g.lower = 1;
+    g.subtract = 1;
+    g.state = D.state;
+    LAUNCH(launch_gemm_nt(g, (D.MT - k) / kTile, ncols / kTile, D.batch, ctx->stream));
+    const double w = (double)ncols, m = (double)(D.MT - k);
+    D.flops += (double)k * (w * w + 2.0 * (m - w) * w);
+    return CHEQ_OK;
+}
+
+int backsolve(Dense& D, int NP, double* v, long v_stride) {
+    cheq_ctx* ctx = D.ctx;
+    for (int kb = NP / kTile - 1; kb >= 0; --kb)
+        LAUNCH(launch_backsolve_step(D.A, D.ld, D.strideA, D.Linv, D.strideLinv, NP, kb, v, v_stride,
+                                     ctx->scratch.as<double>(), (long)backsolve_max_ctas() * kTile,
+                                     ctx->counters.as<unsigned>(), D.state, D.batch, ctx->stream));
+    return CHEQ_OK;
+}
+
+int ensure_host_state(cheq_ctx* ctx, size_t batch) {
+    if (batch <= ctx->h_state_cap) return CHEQ_OK;
+    if (ctx->h_state) cudaFreeHost(ctx->h_state);
+    ctx->h_state = nullptr;
+    CU(cudaMallocHost((void**)&ctx->h_state, batch * sizeof(ScfState)));
+    ctx->h_state_cap = batch;
+    return CHEQ_OK;
+}
+
+struct SolveIO {
+    bool device_ptrs = false;
+    long n = 0;
+    long frames = 1;
+    const double *xyz = nullptr, *chi = nullptr, *hard = nullptr, *radius = nullptr;
+    const uint8_t* nq = nullptr;
+    double total_charge = 0.0;
+    const cheq_options* opt = nullptr;
+    const cheq_external* ext = nullptr;
+    double* charges_out = nullptr;
+    double* potential_out = nullptr;
+    uint32_t* iterations_out = nullptr;
+    double* delta_out = nullptr;
+    int32_t* status_out = nullptr;   // batch only
+};
+
+int validate_options(cheq_ctx* ctx, const cheq_options* o) {
+    if (!o) return fail(ctx, CHEQ_ERR_INVALID_ARGUMENT, "options is NULL");
+    if (o->basis > 1) return fail(ctx, CHEQ_ERR_INVALID_ARGUMENT, "unknown basis");
+    if (o->damping_kind > 2) return fail(ctx, CHEQ_ERR_INVALID_ARGUMENT, "unknown damping kind");
+    return CHEQ_OK;
+}
+
+bool external_is_empty(const cheq_external* e) {
+    // types.rs:281-286
+    return !e || (e->num_point_charges == 0 && e->field[0] == 0.0 && e->field[1] == 0.0 && e->field[2] == 0.0);
+}
+
+// Uploads inputs, builds layout + tables, gathers to internal order, runs v_ext and the assembly.
+// On return the matrix and right-hand-side rows of every frame of the chunk are in ctx->A.
+struct Prepared {
+    Layout L;
+    PairTableView view{};
+    int blob_bytes = 0;
+    long strideA = 0;
+    int batch = 1;
+};
+
+int prepare_and_assemble(cheq_ctx* ctx, const SolveIO& io, long frame0, int batch, bool hydrogen_scf,
+                         Prepared& P, bool topology_ready) {
+    const long n = io.n;
+    const cheq_options& o = *io.opt;
+    cudaStream_t st = ctx->stream;
+    const bool has_ext = !external_is_empty(io.ext);
+    const long m = has_ext ? (long)io.ext->num_point_charges : 0;
+    auto t_host = Clock::now();
+
+    if (!topology_ready) {
+        std::vector<double> h_radius, h_pc_radius;
+        std::vector<uint8_t> h_nq, h_pc_n;
+        const double* radius = io.radius;
+        const uint8_t* nq = io.nq;
+        const double* pc_radius = has_ext ? io.ext->radius : nullptr;
+        const uint8_t* pc_n = has_ext ? io.ext->n : nullptr;
+        if (io.device_ptrs) {
+            h_radius.resize(n);
+            h_nq.resize(n);
+            CU(cudaMemcpy(h_radius.data(), io.radius, n * 8, cudaMemcpyDeviceToHost));
+            CU(cudaMemcpy(h_nq.data(), io.nq, n, cudaMemcpyDeviceToHost));
+            radius = h_radius.data();
+            nq = h_nq.data();
+            if (m > 0) {
+                h_pc_radius.resize(m);
+                h_pc_n.resize(m);
+                CU(cudaMemcpy(h_pc_radius.data(), io.ext->radius, m * 8, cudaMemcpyDeviceToHost));
+                CU(cudaMemcpy(h_pc_n.data(), io.ext->n, m, cudaMemcpyDeviceToHost));
+                pc_radius = h_pc_radius.data();
+                pc_n = h_pc_n.data();
+            }
+        }
+        std::vector<int> pc_type;
+        int rc = make_layout(ctx, n, radius, nq, hydrogen_scf, pc_radius, pc_n, m, P.L, pc_type);
+        if (rc) return rc;
+        PackedTables pk;
+        rc = pack_tables(ctx, P.L.types, o.lambda_scale, o.basis, pk);
+        if (rc) return rc;
+        ctx->stats.pair_types = pk.pair_types;
+        rc = upload_tables(ctx, pk, P.view);
+        if (rc) return rc;
+        P.blob_bytes = (int)pk.blob.size();
+        CU(ctx->perm.ensure(P.L.NP * sizeof(int)));
+        CU(ctx->type.ensure(P.L.NP));
+        CU(cudaMemcpyAsync(ctx->perm.p, P.L.perm.data(), P.L.NP * sizeof(int), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->type.p, P.L.type.data(), P.L.NP, cudaMemcpyHostToDevice, st));
+        if (m > 0) {
+            CU(ctx->pc_type.ensure(m * sizeof(int)));
+            CU(cudaMemcpyAsync(ctx->pc_type.p, pc_type.data(), m * sizeof(int), cudaMemcpyHostToDevice, st));
+        }
+        // the async copies above read pageable host vectors that die with this scope
+        CU(cudaStreamSynchronize(st));
+    }
+    const Layout& L = P.L;
+    P.batch = batch;
+    P.strideA = (long)L.ld * L.NP;
+    ctx->stats.n_atoms = n;
+    ctx->stats.n_hydrogen = L.scf ? L.nh : 0;
+    ctx->stats.n_padded = L.NP;
+    ctx->stats.ms_host_prepare += ms_since(t_host);
+
+    // memory budget
+    {
+        size_t need = (size_t)P.strideA * 8 * batch;
+        if (L.scf) need += (size_t)(L.MT - L.nxp) * L.nhp * 8 * batch;
+        need += (size_t)L.NP * kTile * 8 * batch;
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        const size_t have = free_b + ctx->A.cap + ctx->S0.cap + ctx->Linv.cap;
+        if (need > have)
+            return fail(ctx, CHEQ_ERR_OUT_OF_MEMORY, "workspace of " + std::to_string(need >> 20) +
+                                                         " MiB exceeds free device memory");
+    }
+    CU(ctx->A.ensure((size_t)P.strideA * 8 * batch));
+    if (L.scf) CU(ctx->S0.ensure((size_t)(L.MT - L.nxp) * L.nhp * 8 * batch));
+    CU(ctx->Linv.ensure((size_t)L.NP * kTile * 8 * batch));
+    const size_t vec = (size_t)L.NP * 8 * batch;
+    CU(ctx->x.ensure(vec));
+    CU(ctx->y.ensure(vec));
+    CU(ctx->z.ensure(vec));
+    CU(ctx->v.ensure(vec));
+    CU(ctx->q.ensure(vec));
+    CU(ctx->diag.ensure(L.NP * 8));
+    CU(ctx->chi.ensure(L.NP * 8));
+    CU(ctx->hard.ensure(L.NP * 8));
+    CU(ctx->scratch.ensure((size_t)backsolve_max_ctas() * kTile * 8 * batch));
+    CU(ctx->counters.ensure(sizeof(unsigned) * batch));
+    CU(ctx->state.ensure(sizeof(ScfState) * batch));
+    CU(ctx->active.ensure(sizeof(int)));
+    int rc = ensure_host_state(ctx, batch);
+    if (rc) return rc;
+    if (!ctx->h_active) CU(cudaMallocHost((void**)&ctx->h_active, sizeof(int)));
+    CU(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned) * batch, st));
+    CU(cudaMemsetAsync(ctx->q.p, 0, vec, st));
+
+    // inputs -> device
+    CU(cudaEventRecord(ctx->ev[0], st));
+    const double *d_xyz, *d_chi, *d_hard;
+    if (io.device_ptrs) {
+        d_xyz = io.xyz + frame0 * n * 3;
+        d_chi = io.chi;
+        d_hard = io.hard;
+    } else {
+        CU(ctx->in_xyz.ensure((size_t)n * 24 * batch));
+        CU(ctx->in_chi.ensure(n * 8));
+        CU(ctx->in_hard.ensure(n * 8));
+        CU(cudaMemcpyAsync(ctx->in_xyz.p, io.xyz + frame0 * n * 3, (size_t)n * 24 * batch, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->in_chi.p, io.chi, n * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->in_hard.p, io.hard, n * 8, cudaMemcpyHostToDevice, st));
+        d_xyz = ctx->in_xyz.as<double>();
+        d_chi = ctx->in_chi.as<double>();
+        d_hard = ctx->in_hard.as<double>();
+    }
+    const double *d_pc_xyz = nullptr, *d_pc_q = nullptr;
+    if (m > 0) {
+        if (io.device_ptrs) {
+            d_pc_xyz = io.ext->xyz;
+            d_pc_q = io.ext->charge;
+        } else {
+            CU(ctx->pc_xyz.ensure(m * 24));
+            CU(ctx->pc_q.ensure(m * 8));
+            CU(cudaMemcpyAsync(ctx->pc_xyz.p, io.ext->xyz, m * 24, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(ctx->pc_q.p, io.ext->charge, m * 8, cudaMemcpyHostToDevice, st));
+            d_pc_xyz = ctx->pc_xyz.as<double>();
+            d_pc_q = ctx->pc_q.as<double>();
+        }
+    }
+    CU(cudaEventRecord(ctx->ev[1], st));
+
+    GatherArgs ga{};
+    ga.NP = L.NP;
+    ga.n = n;
+    ga.pos_stride = L.NP;
+    ga.perm = ctx->perm.as<int>();
+    ga.xyz_in = d_xyz;
+    ga.chi_in = d_chi;
+    ga.hard_in = d_hard;
+    ga.x = ctx->x.as<double>();
+    ga.y = ctx->y.as<double>();
+    ga.z = ctx->z.as<double>();
+    ga.diag = ctx->diag.as<double>();
+    ga.chi = ctx->chi.as<double>();
+    ga.hard = ctx->hard.as<double>();
+    LAUNCH(launch_gather(ga, batch, st));
+
+    const double* d_vext = nullptr;
+    if (has_ext) {
+        CU(ctx->vext.ensure(L.NP * 8));
+        VextArgs va{};
+        va.x = ctx->x.as<double>();
+        va.y = ctx->y.as<double>();
+        va.z = ctx->z.as<double>();
+        va.type = ctx->type.as<uint8_t>();
+        va.NP = L.NP;
+        va.m = m;
+        va.pc_xyz = d_pc_xyz;
+        va.pc_charge = d_pc_q;
+        va.pc_type = ctx->pc_type.as<int>();
+        va.field[0] = io.ext->field[0];
+        va.field[1] = io.ext->field[1];
+        va.field[2] = io.ext->field[2];
+        va.v_out = ctx->vext.as<double>();
+        LAUNCH(launch_vext(va, P.view, ctx->blob.as<char>(), P.blob_bytes, st));
+        d_vext = ctx->vext.as<double>();
+    }
+
+    AssembleArgs aa{};
+    aa.x = ctx->x.as<double>();
+    aa.y = ctx->y.as<double>();
+    aa.z = ctx->z.as<double>();
+    aa.type = ctx->type.as<uint8_t>();
+    aa.diag = ctx->diag.as<double>();
+    aa.A = ctx->A.as<double>();
+    aa.ld = L.ld;
+    aa.a_stride = P.strideA;
+    aa.pos_stride = L.NP;
+    aa.NP = L.NP;
+    LAUNCH(launch_assemble(aa, P.view, ctx->blob.as<char>(), P.blob_bytes, batch, st));
+    LAUNCH(launch_rhs_rows(ctx->A.as<double>(), L.ld, P.strideA, L.NP, ctx->chi.as<double>(), d_vext, 0,
+                           ctx->type.as<uint8_t>(), batch, st));
+    CU(cudaEventRecord(ctx->ev[2], st));
+    ctx->stats.bytes_assemble += 8.0 * (double)n * (double)(n + 1) / 2.0 * batch;
+    return CHEQ_OK;
+}
+
+// Factorisation + SCF for the frames currently assembled in ctx->A.  Fills h_state[0..batch).
+int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
+    const Layout& L = P.L;
+    const cheq_options& o = *io.opt;
+    cudaStream_t st = ctx->stream;
+    const int batch = P.batch;
+    Dense D{ctx, ctx->A.as<double>(), L.ld, P.strideA, ctx->Linv.as<double>(), (long)L.NP * kTile, L.MT,
+            ctx->state.as<ScfState>(), batch};
+    double damping0 = 1.0;   // implementation.rs:297-301
+    if (L.scf && o.damping_kind != CHEQ_DAMPING_NONE) damping0 = o.damping_value;
+    LAUNCH(launch_scf_init(ctx->state.as<ScfState>(), damping0, batch, st));
+    double* v = ctx->v.as<double>();
+    double* q = ctx->q.as<double>();
+    int rc;
+
+    if (!L.scf) {
+        // implementation.rs:284-292: one solve, iterations = 1, charges = raw solution
+        rc = factor_panel(D, 0, L.NP);
+        if (rc) return rc;
+        CU(cudaEventRecord(ctx->ev[3], st));
+        LAUNCH(launch_mu(D.A, D.ld, D.strideA, L.NP, io.total_charge, v, L.NP, D.state, batch, st));
+        rc = backsolve(D, L.NP, v, L.NP);
+        if (rc) return rc;
+        LAUNCH(launch_scf_mix(v, q, L.NP, ctx->type.as<uint8_t>(), L.NP, D.state, batch, st));
+        CU(cudaMemsetAsync(ctx->active.p, 0, sizeof(int), st));
+        LAUNCH(launch_scf_decide(D.state, INFINITY, CHEQ_DAMPING_NONE, batch, ctx->active.as<int>(), st));
+        CU(cudaMemcpyAsync(ctx->h_state, ctx->state.p, sizeof(ScfState) * batch, cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(ctx->ev[4], st));
+        CU(cudaStreamSynchronize(st));
+        ctx->stats.flops_factor += D.flops * batch;
+        return CHEQ_OK;
+    }
+
+    // geometry-invariant part: factor the non-hydrogen block, form the hydrogen Schur complement S0 and the
+    // reduced right-hand sides; snapshot them.
+    rc = factor_panel(D, 0, L.nxp);
+    if (rc) return rc;
+    rc = schur_update(D, L.nxp, L.nhp);
+    if (rc) return rc;
+    const long ld0 = L.MT - L.nxp;
+    const long stride0 = ld0 * L.nhp;
+    double* Ahh = D.A + (long)L.nxp + (long)L.nxp * L.ld;
+    const int mt_h = (L.MT - L.nxp) / kTile, nt_h = L.nhp / kTile;
+    LAUNCH(launch_copy_lower_tiles(Ahh, L.ld, D.strideA, ctx->S0.as<double>(), ld0, stride0, mt_h, nt_h, nullptr,
+                                   batch, st));
+    CU(cudaEventRecord(ctx->ev[3], st));
+    const double flops_once = D.flops;
+    D.flops = 0.0;
+
+    const uint8_t* type_h = ctx->type.as<uint8_t>() + L.nxp;
+    const double* hard_h = ctx->hard.as<double>() + L.nxp;
+    uint32_t it = 0;
+    double flops_iter_total = 0.0;
+    for (it = 1; it <= o.max_iterations; ++it) {
+        if (it > 1)
+            LAUNCH(launch_copy_lower_tiles(ctx->S0.as<double>(), ld0, stride0, Ahh, L.ld, D.strideA, mt_h, nt_h,
+                                           D.state, batch, st));
+        LAUNCH(launch_set_h_diagonal(Ahh, L.ld, D.strideA, ctx->S0.as<double>(), ld0, stride0, hard_h,
+                                     q + L.nxp, L.NP, type_h, L.nhp, D.state, batch, st));
+        D.flops = 0.0;
+        rc = factor_panel(D, L.nxp, L.nhp);
+        if (rc) return rc;
+        LAUNCH(launch_mu(D.A, D.ld, D.strideA, L.NP, io.total_charge, v, L.NP, D.state, batch, st));
+        rc = backsolve(D, L.NP, v, L.NP);
+        if (rc) return rc;
+        LAUNCH(launch_scf_mix(v, q, L.NP, ctx->type.as<uint8_t>(), L.NP, D.state, batch, st));
+        CU(cudaMemsetAsync(ctx->active.p, 0, sizeof(int), st));
+        LAUNCH(launch_scf_decide(D.state, o.tolerance, o.damping_kind, batch, ctx->active.as<int>(), st));
+        CU(cudaMemcpyAsync(ctx->h_active, ctx->active.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        flops_iter_total += D.flops * (double)batch;   // upper bound for batches (finished frames skip)
+        if (*ctx->h_active == 0) break;
+    }
+    CU(cudaMemcpyAsync(ctx->h_state, ctx->state.p, sizeof(ScfState) * batch, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(ctx->ev[4], st));
+    CU(cudaStreamSynchronize(st));
+    ctx->stats.flops_factor += flops_once * batch + flops_iter_total;
+    return CHEQ_OK;
+}
+
+int frame_status(const ScfState& s) {
+    if (s.info != 0) return CHEQ_ERR_LINALG;
+    if (!std::isfinite(s.mu)) return CHEQ_ERR_LINALG;
+    if (!s.converged && s.active) return CHEQ_ERR_NOT_CONVERGED;   // still active when the loop ran out
+    return CHEQ_OK;
+}
+
+// Pivoted-LU path for ONE frame whose matrix is not positive definite: the reference's algorithm as written
+// (fresh partial-pivot LU of the bordered matrix every SCF iteration, implementation.rs:303-314, 574-576).
+// Expects a fresh assembly of that frame in ctx->A.
+int lu_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
+    const Layout& L = P.L;
+    const cheq_options& o = *io.opt;
+    cudaStream_t st = ctx->stream;
+    const int n1p = lu_padded_size(L.NP);
+    CU(ctx->lu_f.ensure((size_t)n1p * (n1p + 1) * 8));
+    CU(ctx->lu_piv.ensure((size_t)n1p * sizeof(int)));
+    ScfState* state = ctx->state.as<ScfState>();
+    double damping0 = 1.0;
+    if (L.scf && o.damping_kind != CHEQ_DAMPING_NONE) damping0 = o.damping_value;
+    LAUNCH(launch_scf_init(state, damping0, 1, st));
+    CU(cudaMemsetAsync(ctx->q.p, 0, (size_t)L.NP * 8, st));
+    double* v = ctx->v.as<double>();
+    double* q = ctx->q.as<double>();
+    unsigned long long launches = 0;
+    const uint32_t max_it = L.scf ? o.max_iterations : 1;
+    for (uint32_t it = 1; it <= max_it; ++it) {
+        CU(launch_lu_solve(ctx->A.as<double>(), L.ld, L.NP, L.nxp, L.scf ? 1 : 0, ctx->lu_f.as<double>(), q,
+                           ctx->hard.as<double>(), ctx->type.as<uint8_t>(), io.total_charge,
+                           ctx->lu_piv.as<int>(), v, state, &launches, st));
+        LAUNCH(launch_scf_mix(v, q, L.NP, ctx->type.as<uint8_t>(), L.NP, state, 1, st));
+        CU(cudaMemsetAsync(ctx->active.p, 0, sizeof(int), st));
+        LAUNCH(launch_scf_decide(state, L.scf ? o.tolerance : INFINITY, L.scf ? o.damping_kind : CHEQ_DAMPING_NONE,
+                                 1, ctx->active.as<int>(), st));
+        CU(cudaMemcpyAsync(ctx->h_active, ctx->active.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (*ctx->h_active == 0) break;
+    }
+    ctx->launches += launches;
+    CU(cudaMemcpyAsync(ctx->h_state, ctx->state.p, sizeof(ScfState), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return CHEQ_OK;
+}
+
+// Scatter + download the charges of `batch` frames starting at global frame gf0, and fill the scalar outputs.
+int emit_results(cheq_ctx* ctx, const SolveIO& io, const Prepared& P, long gf0, int batch, int* worst) {
+    cudaStream_t st = ctx->stream;
+    const long n = io.n;
+    double* d_out;
+    if (io.device_ptrs) {
+        d_out = io.charges_out + gf0 * n;
+    } else {
+        CU(ctx->out_q.ensure((size_t)n * 8 * batch));
+        d_out = ctx->out_q.as<double>();
+    }
+    LAUNCH(launch_scatter_charges(P.L.NP, ctx->perm.as<int>(), ctx->q.as<double>(), P.L.NP, d_out, n, batch, st));
+    CU(cudaEventRecord(ctx->ev[5], st));
+    if (!io.device_ptrs)
+        CU(cudaMemcpyAsync(io.charges_out + gf0 * n, d_out, (size_t)n * 8 * batch, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(ctx->ev[6], st));
+    CU(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[5], ctx->ev[6]);
+    ctx->stats.ms_d2h += ms;
+    for (int f = 0; f < batch; ++f) {
+        const ScfState& s = ctx->h_state[f];
+        const int fs = frame_status(s);
+        const long gf = gf0 + f;
+        if (io.potential_out) io.potential_out[gf] = s.mu;
+        if (io.iterations_out) io.iterations_out[gf] = P.L.scf ? (uint32_t)s.iteration : 1u;
+        if (io.delta_out) io.delta_out[gf] = s.delta;
+        if (io.status_out) io.status_out[gf] = fs;
+        if (fs != CHEQ_OK && *worst == CHEQ_OK) {
+            *worst = fs;
+            if (fs == CHEQ_ERR_LINALG) {
+                ctx->err = "Linear system solver panicked. Matrix might be singular.";
+            } else {
+                char buf[160];
+                snprintf(buf, sizeof buf, "SCF failed to converge after %u iterations. Final charge difference: %.2e",
+                         io.opt->max_iterations, s.delta);
+                ctx->err = buf;
+            }
+        }
+        ctx->stats.iterations = std::max<uint32_t>(ctx->stats.iterations, P.L.scf ? (uint32_t)s.iteration : 1u);
+    }
+    return CHEQ_OK;
+}
+
+int solve_impl(cheq_ctx* ctx, const SolveIO& io) {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    auto t_total = Clock::now();
+    ctx->err.clear();
+    ctx->stats = cheq_stats{};
+    ctx->launches = 0;
+    if (io.n == 0) return fail(ctx, CHEQ_ERR_NO_ATOMS, "Input validation failed: at least one atom is required for a calculation");
+    int rc = validate_options(ctx, io.opt);
+    if (rc) return rc;
+    if (!io.xyz || !io.chi || !io.hard || !io.radius || !io.nq || !io.charges_out)
+        return fail(ctx, CHEQ_ERR_INVALID_ARGUMENT, "NULL array argument");
+    if (io.n > 2000000) return fail(ctx, CHEQ_ERR_INVALID_ARGUMENT, "too many atoms for a dense solve");
+    CU(cudaSetDevice(ctx->device));
+    const long n = io.n;
+
+    // frames per chunk from the memory budget (single solve: 1)
+    long chunk = 1;
+    Prepared P;
+    if (io.frames > 1) {
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        const long NPmax = round_up_tile((int)n) + kTile;
+        const double per_frame = 8.0 * ((double)(NPmax + kRhsRows) * NPmax * 2.0 + (double)NPmax * kTile + 8.0 * NPmax);
+        const double budget = 0.8 * (double)(free_b + ctx->A.cap + ctx->S0.cap + ctx->Linv.cap);
+        chunk = std::max<long>(1, std::min<long>(io.frames, (long)(budget / per_frame)));
+        chunk = std::min<long>(chunk, 4096);
+    }
+    bool topo_ready = false;
+    int worst = CHEQ_OK;
+    for (long f0 = 0; f0 < io.frames; f0 += chunk) {
+        const int batch = (int)std::min<long>(chunk, io.frames - f0);
+        rc = prepare_and_assemble(ctx, io, f0, batch, io.opt->hydrogen_scf != 0, P, topo_ready);
+        if (rc) return rc;
+        topo_ready = true;
+        rc = factor_and_scf(ctx, io, P);
+        if (rc) return rc;
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+        ctx->stats.ms_h2d += ms;
+        cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
+        ctx->stats.ms_assemble += ms;
+        cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]);
+        ctx->stats.ms_factor_once += ms;
+        cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]);
+        ctx->stats.ms_scf += ms;
+        std::vector<int> not_spd;
+        for (int f = 0; f < batch; ++f)
+            if (ctx->h_state[f].info != 0) not_spd.push_back(f);
+        if (batch == 1 && !not_spd.empty()) {
+            // single solve: redo with the pivoted LU
+            rc = prepare_and_assemble(ctx, io, f0, 1, io.opt->hydrogen_scf != 0, P, true);
+            if (rc) return rc;
+            rc = lu_scf(ctx, io, P);
+            if (rc) return rc;
+            ctx->stats.lu_fallback_frames += 1;
+            not_spd.clear();
+        }
+        int chunk_worst = CHEQ_OK;
+        rc = emit_results(ctx, io, P, f0, batch, not_spd.empty() ? &worst : &chunk_worst);
+        if (rc) return rc;
+        // batched frames that were not positive definite: one LU solve each, results overwrite the frame's slots
+        for (int f : not_spd) {
+            rc = prepare_and_assemble(ctx, io, f0 + f, 1, io.opt->hydrogen_scf != 0, P, true);
+            if (rc) return rc;
+            rc = lu_scf(ctx, io, P);
+            if (rc) return rc;
+            ctx->stats.lu_fallback_frames += 1;
+            rc = emit_results(ctx, io, P, f0 + f, 1, &worst);
+            if (rc) return rc;
+        }
+        if (!not_spd.empty()) {
+            // statuses of the other frames of this chunk were written by the first emit; fold them into `worst`
+            if (io.status_out)
+                for (int f = 0; f < batch; ++f)
+                    if (io.status_out[f0 + f] != CHEQ_OK && worst == CHEQ_OK) worst = io.status_out[f0 + f];
+        }
+    }
+    ctx->stats.kernel_launches = ctx->launches;
+    ctx->stats.ms_total = ms_since(t_total);
+    if (io.frames > 1 && io.status_out) return CHEQ_OK;
+    return worst;
+}
+
+}  // namespace
+
+// ================================================================================================================
+extern "C" {
+
+int32_t cheq_ctx_create(int32_t device, cheq_ctx** out) {
+    if (!out) return CHEQ_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return CHEQ_ERR_CUDA;   // no CPU fallback by design
+    }
+    if (device < 0 || device >= count) return CHEQ_ERR_INVALID_ARGUMENT;
+    if (cudaSetDevice(device) != cudaSuccess) return CHEQ_ERR_CUDA;
+    cheq_ctx* ctx = new cheq_ctx();
+    ctx->device = device;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return CHEQ_ERR_CUDA;
+    }
+    for (auto& e : ctx->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) {
+            delete ctx;
+            return CHEQ_ERR_CUDA;
+        }
+    *out = ctx;
+    return CHEQ_OK;
+}
+
+void cheq_ctx_destroy(cheq_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    DeviceBuffer* bufs[] = {&ctx->in_xyz, &ctx->in_chi, &ctx->in_hard, &ctx->in_radius, &ctx->in_nq, &ctx->perm,
+                            &ctx->type, &ctx->x, &ctx->y, &ctx->z, &ctx->diag, &ctx->chi, &ctx->hard, &ctx->vext,
+                            &ctx->A, &ctx->S0, &ctx->Linv, &ctx->v, &ctx->q, &ctx->scratch, &ctx->counters,
+                            &ctx->state, &ctx->active, &ctx->blob, &ctx->pc_xyz, &ctx->pc_q, &ctx->pc_type,
+                            &ctx->out_q, &ctx->misc0, &ctx->misc1, &ctx->misc2, &ctx->lu_f, &ctx->lu_piv};
+    for (DeviceBuffer* b : bufs) b->release();
+    if (ctx->h_state) cudaFreeHost(ctx->h_state);
+    if (ctx->h_active) cudaFreeHost(ctx->h_active);
+    for (auto& e : ctx->ev)
+        if (e) cudaEventDestroy(e);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* cheq_last_error(const cheq_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+void cheq_options_default(cheq_options* o) {
+    if (!o) return;
+    // options.rs:90-100
+    o->tolerance = 1.0e-6;
+    o->lambda_scale = 0.5;
+    o->damping_value = 0.4;
+    o->max_iterations = 2000;
+    o->hydrogen_scf = 1;
+    o->basis = CHEQ_BASIS_STO;
+    o->damping_kind = CHEQ_DAMPING_AUTO;
+    o->reserved = 0;
+}
+
+int32_t cheq_get_stats(const cheq_ctx* ctx, cheq_stats* out) {
+    if (!ctx || !out) return CHEQ_ERR_INVALID_ARGUMENT;
+    *out = ctx->stats;
+    return CHEQ_OK;
+}
+
+void* cheq_ctx_stream(const cheq_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int32_t cheq_solve(cheq_ctx* ctx, uint64_t n_atoms, const double* xyz, const double* chi, const double* hardness,
+                   const double* radius, const uint8_t* n_quantum, double total_charge, const cheq_options* options,
+                   const cheq_external* external, double* charges_out, double* potential_out,
+                   uint32_t* iterations_out, double* delta_out) {
+    if (!ctx) return CHEQ_ERR_INVALID_ARGUMENT;
+    SolveIO io;
+    io.n = (long)n_atoms;
+    io.xyz = xyz;
+    io.chi = chi;
+    io.hard = hardness;
+    io.radius = radius;
+    io.nq = n_quantum;
+    io.total_charge = total_charge;
+    io.opt = options;
+    io.ext = external;
+    io.charges_out = charges_out;
+    io.potential_out = potential_out;
+    io.iterations_out = iterations_out;
+    io.delta_out = delta_out;
+    return solve_impl(ctx, io);
+}
+
+int32_t cheq_solve_device(cheq_ctx* ctx, uint64_t n_atoms, const double* d_xyz, const double* d_chi,
+                          const double* d_hardness, const double* d_radius, const uint8_t* d_n_quantum,
+                          double total_charge, const cheq_options* options, const cheq_external* d_external,
+                          double* d_charges_out, double* potential_out, uint32_t* iterations_out,
+                          double* delta_out) {
+    if (!ctx) return CHEQ_ERR_INVALID_ARGUMENT;
+    SolveIO io;
+    io.device_ptrs = true;
+    io.n = (long)n_atoms;
+    io.xyz = d_xyz;
+    io.chi = d_chi;
+    io.hard = d_hardness;
+    io.radius = d_radius;
+    io.nq = d_n_quantum;
+    io.total_charge = total_charge;
+    io.opt = options;
+    io.ext = d_external;
+    io.charges_out = d_charges_out;
+    io.potential_out = potential_out;
+    io.iterations_out = iterations_out;
+    io.delta_out = delta_out;
+    return solve_impl(ctx, io);
+}
+
+int32_t cheq_solve_batch(cheq_ctx* ctx, uint64_t n_frames, uint64_t n_atoms, const double* xyz, const double* chi,
+                         const double* hardness, const double* radius, const uint8_t* n_quantum,
+                         double total_charge, const cheq_options* options, double* charges_out,
+                         double* potential_out, uint32_t* iterations_out, double* delta_out, int32_t* status_out) {
+    if (!ctx) return CHEQ_ERR_INVALID_ARGUMENT;
+    if (n_frames == 0) return CHEQ_OK;
+    SolveIO io;
+    io.n = (long)n_atoms;
+    io.frames = (long)n_frames;
+    io.xyz = xyz;
+    io.chi = chi;
+    io.hard = hardness;
+    io.radius = radius;
+    io.nq = n_quantum;
+    io.total_charge = total_charge;
+    io.opt = options;
+    io.charges_out = charges_out;
+    io.potential_out = potential_out;
+    io.iterations_out = iterations_out;
+    io.delta_out = delta_out;
+    io.status_out = status_out;
+    return solve_impl(ctx, io);
+}
+
+// ---- component entry points -------------------------------------------------------------------------------------
+
+int32_t cheq_pair_integrals(cheq_ctx* ctx, uint64_t count, const double* distance, const uint8_t* n1,
+                            const double* radius1, const uint8_t* n2, const double* radius2, double lambda_scale,
+                            uint8_t basis, double* out_ev) {
+    if (!ctx) return CHEQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->err.clear();
+    ctx->launches = 0;
+    if (count == 0) return CHEQ_OK;
+    if (basis > 1) return fail(ctx, CHEQ_ERR_INVALID_ARGUMENT, "unknown basis");
+    CU(cudaSetDevice(ctx->device));
+    std::vector<ElementType> types;
+    std::map<std::pair<uint8_t, uint64_t>, int> index;
+    std::vector<int> ti(count), tj(count);
+    for (uint64_t k = 0; k < count; ++k) {
+        ti[k] = find_or_add_type(types, index, n1[k], radius1[k]);
+        tj[k] = find_or_add_type(types, index, n2[k], radius2[k]);
+    }
+    PackedTables pk;
+    int rc = pack_tables(ctx, types, lambda_scale, basis, pk);
+    if (rc) return rc;
+    PairTableView view;
+    rc = upload_tables(ctx, pk, view);
+    if (rc) return rc;
+    CU(ctx->misc0.ensure(count * 8));
+    CU(ctx->misc1.ensure(count * 8));
+    CU(ctx->misc2.ensure(count * 8));
+    int* d_ti = ctx->misc1.as<int>();
+    int* d_tj = d_ti + count;
+    cudaStream_t st = ctx->stream;
+    CU(cudaMemcpyAsync(ctx->misc0.p, distance, count * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_ti, ti.data(), count * 4, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(d_tj, tj.data(), count * 4, cudaMemcpyHostToDevice, st));
+    LAUNCH(launch_pair_list((long)count, ctx->misc0.as<double>(), d_ti, d_tj, view, ctx->misc2.as<double>(), st));
+    CU(cudaMemcpyAsync(out_ev, ctx->misc2.p, count * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return CHEQ_OK;
+}
+
+int32_t cheq_assemble_matrix(cheq_ctx* ctx, uint64_t n_atoms, const double* xyz, const double* hardness,
+                             const double* radius, const uint8_t* n_quantum, double lambda_scale, uint8_t basis,
+                             double* matrix_out) {
+    if (!ctx) return CHEQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->err.clear();
+    ctx->stats = cheq_stats{};
+    ctx->launches = 0;
+    if (n_atoms == 0) return fail(ctx, CHEQ_ERR_NO_ATOMS, "no atoms");
+    CU(cudaSetDevice(ctx->device));
+    cheq_options o;
+    cheq_options_default(&o);
+    o.lambda_scale = lambda_scale;
+    o.basis = basis;
+    std::vector<double> chi(n_atoms, 0.0);
+    SolveIO io;
+    io.n = (long)n_atoms;
+    io.xyz = xyz;
+    io.chi = chi.data();
+    io.hard = hardness;
+    io.radius = radius;
+    io.nq = n_quantum;
+    io.opt = &o;
+    Prepared P;
+    int rc = prepare_and_assemble(ctx, io, 0, 1, true, P, false);
+    if (rc) return rc;
+    const long n = (long)n_atoms;
+    CU(ctx->misc0.ensure((size_t)n * n * 8));
+    LAUNCH(launch_export_matrix(P.L.NP, P.L.ld, ctx->A.as<double>(), ctx->perm.as<int>(), n, ctx->misc0.as<double>(),
+                                ctx->stream));
+    CU(cudaMemcpyAsync(matrix_out, ctx->misc0.p, (size_t)n * n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
+    ctx->stats.ms_assemble = ms;
+    ctx->stats.kernel_launches = ctx->launches;
+    return CHEQ_OK;
+}
+
+int32_t cheq_external_potential(cheq_ctx* ctx, uint64_t n_atoms, const double* xyz, const double* radius,
+                                const uint8_t* n_quantum, const cheq_external* external, double lambda_scale,
+                                uint8_t basis, double* v_out) {
+    if (!ctx) return CHEQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->err.clear();
+    ctx->launches = 0;
+    if (n_atoms == 0) return fail(ctx, CHEQ_ERR_NO_ATOMS, "no atoms");
+    if (!external) return fail(ctx, CHEQ_ERR_INVALID_ARGUMENT, "external is NULL");
+    CU(cudaSetDevice(ctx->device));
+    cheq_options o;
+    cheq_options_default(&o);
+    o.lambda_scale = lambda_scale;
+    o.basis = basis;
+    const long n = (long)n_atoms;
+    std::vector<double> zeros(n, 0.0), ones(n, 1.0);
+    cheq_external ext = *external;
+    // a zero field with no charges would be "empty"; force evaluation with an explicit flag instead
+    SolveIO io;
+    io.n = n;
+    io.xyz = xyz;
+    io.chi = zeros.data();
+    io.hard = ones.data();
+    io.radius = radius;
+    io.nq = n_quantum;
+    io.opt = &o;
+    io.ext = &ext;
+    Prepared P;
+    if (external_is_empty(&ext)) {
+        for (long i = 0; i < n; ++i) v_out[i] = 0.0;
+        return CHEQ_OK;
+    }
+    int rc = prepare_and_assemble(ctx, io, 0, 1, false, P, false);
+    if (rc) return rc;
+    CU(ctx->out_q.ensure(n * 8));
+    LAUNCH(launch_scatter_charges(P.L.NP, ctx->perm.as<int>(), ctx->vext.as<double>(), P.L.NP,
+                                  ctx->out_q.as<double>(), n, 1, ctx->stream));
+    CU(cudaMemcpyAsync(v_out, ctx->out_q.p, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return CHEQ_OK;
+}
+
+int32_t cheq_dbg_gemm_nt(cheq_ctx* ctx, uint64_t m, uint64_t n, uint64_t k, const double* a, const double* b,
+                         double* c, int32_t subtract) {
+    if (!ctx) return CHEQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->err.clear();
+    if (m % kTile || n % kTile || k % kTile || !m || !n || !k)
+        return fail(ctx, CHEQ_ERR_INVALID_ARGUMENT, "m, n, k must be positive multiples of 128");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CU(ctx->misc0.ensure(m * k * 8));
+    CU(ctx->misc1.ensure(n * k * 8));
+    CU(ctx->misc2.ensure(m * n * 8));
+    CU(cudaMemcpyAsync(ctx->misc0.p, a, m * k * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->misc1.p, b, n * k * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->misc2.p, c, m * n * 8, cudaMemcpyHostToDevice, st));
+    GemmArgs g{};
+    g.A = ctx->misc0.as<double>();
+    g.lda = (long)m;
+    g.B = ctx->misc1.as<double>();
+    g.ldb = (long)n;
+    g.C = ctx->misc2.as<double>();
+    g.ldc = (long)m;
+    g.K = (int)k;
+    g.lower = 0;
+    g.subtract = subtract ? 1 : 0;
+    LAUNCH(launch_gemm_nt(g, (int)(m / kTile), (int)(n / kTile), 1, st));
+    CU(cudaMemcpyAsync(c, ctx->misc2.p, m * n * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    return CHEQ_OK;
+}
+
+int32_t cheq_dbg_cholesky_solve(cheq_ctx* ctx, uint64_t n_, const double* a, uint64_t nrhs, const double* b,
+                                double* x_out, double* l_out) {
+    if (!ctx) return CHEQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->err.clear();
+    ctx->launches = 0;
+    if (n_ == 0 || nrhs == 0 || nrhs > 2) return fail(ctx, CHEQ_ERR_INVALID_ARGUMENT, "need n > 0 and 1 <= nrhs <= 2");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const long n = (long)n_;
+    const int NP = round_up_tile((int)n), MT = NP + kRhsRows;
+    const long ld = MT;
+    // host staging of the padded trapezoid (test path only)
+    std::vector<double> h((size_t)ld * NP, 0.0);
+    for (long j = 0; j < NP; ++j) {
+        if (j < n) {
+            for (long i = j; i < n; ++i) h[i + j * ld] = a[i + j * n];
+            for (uint64_t r = 0; r < nrhs; ++r) h[NP + r + j * ld] = b[j + r * n];
+        } else {
+            h[j + j * ld] = 1.0;
+        }
+    }
+    CU(ctx->A.ensure(h.size() * 8));
+    CU(ctx->Linv.ensure((size_t)NP * kTile * 8));
+    CU(ctx->v.ensure(NP * 8));
+    CU(ctx->scratch.ensure((size_t)backsolve_max_ctas() * kTile * 8));
+    CU(ctx->counters.ensure(sizeof(unsigned)));
+    CU(ctx->state.ensure(sizeof(ScfState)));
+    int rc = ensure_host_state(ctx, 1);
+    if (rc) return rc;
+    CU(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned), st));
+    CU(cudaMemcpyAsync(ctx->A.p, h.data(), h.size() * 8, cudaMemcpyHostToDevice, st));
+    LAUNCH(launch_scf_init(ctx->state.as<ScfState>(), 1.0, 1, st));
+    Dense D{ctx, ctx->A.as<double>(), ld, (long)ld * NP, ctx->Linv.as<double>(), (long)NP * kTile, MT,
+            ctx->state.as<ScfState>(), 1};
+    rc = factor_panel(D, 0, NP);
+    if (rc) return rc;
+    std::vector<double> xv(NP);
+    for (uint64_t r = 0; r < nrhs; ++r) {
+        // v = forward-substituted rhs r (row NP + r)
+        CU(cudaMemcpy2DAsync(ctx->v.p, 8, ctx->A.as<double>() + NP + r, ld * 8, 8, NP, cudaMemcpyDeviceToDevice, st));
+        rc = backsolve(D, NP, ctx->v.as<double>(), NP);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(xv.data(), ctx->v.p, NP * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (long i = 0; i < n; ++i) x_out[i + r * n] = xv[i];
+    }
+    CU(cudaMemcpyAsync(ctx->h_state, ctx->state.p, sizeof(ScfState), cudaMemcpyDeviceToHost, st));
+    if (l_out) {
+        CU(cudaMemcpyAsync(h.data(), ctx->A.p, h.size() * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        for (long j = 0; j < n; ++j)
+            for (long i = 0; i < n; ++i) l_out[i + j * n] = (i >= j) ? h[i + j * ld] : 0.0;
+    }
+    CU(cudaStreamSynchronize(st));
+    ctx->stats.kernel_launches = ctx->launches;
+    if (ctx->h_state[0].info != 0) return fail(ctx, CHEQ_ERR_LINALG, "matrix is not positive definite");
+    return CHEQ_OK;
+}
+
+double cheq_host_sto_table_eval(int32_t n1, double zeta1, int32_t n2, double zeta2, double distance_bohr,
+                                int32_t* kind_out, int32_t* terms_out, int32_t* coefs_out, double* max_abs_err_out) {
+    static std::mutex mu;
+    static std::map<TableKey, StoPairTable> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    TableKey key{n1, n2, bits(zeta1), bits(zeta2)};
+    auto it = cache.find(key);
+    if (it == cache.end()) it = cache.emplace(key, build_sto_pair_table(n1, zeta1, n2, zeta2)).first;
+    const StoPairTable& t = it->second;
+    if (kind_out) *kind_out = t.kind;
+    if (terms_out) *terms_out = (int32_t)t.terms.size();
+    if (coefs_out) {
+        int c = 0;
+        for (const StoTerm& term : t.terms) c += (int)term.coef.size();
+        *coefs_out = c;
+    }
+    if (max_abs_err_out) *max_abs_err_out = t.max_abs_err;
+    return eval_sto_pair_table(t, distance_bohr);
+}
+
+}  // extern "C"

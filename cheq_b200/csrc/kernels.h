@@ -1,0 +1,106 @@
+// Kernel launchers (implemented in kernels_assemble.cu and kernels_dense.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "device_types.h"
+
+namespace cheq {
+
+struct AssembleArgs {
+    const double *x, *y, *z;   // [batch][NP] (pos_stride apart)
+    const uint8_t* type;       // [NP]
+    const double* diag;        // [NP] hardness (1 for padding)
+    double* A;                 // [batch] column-major, ld
+    long ld, a_stride, pos_stride;
+    int NP;
+    int table_smem_bytes;      // filled by the launcher
+};
+
+struct VextArgs {
+    const double *x, *y, *z;
+    const uint8_t* type;
+    int NP;
+    long m;
+    const double* pc_xyz;      // 3 m AoS
+    const double* pc_charge;
+    const int* pc_type;
+    double field[3];
+    double* v_out;
+    int table_smem_bytes;
+};
+
+struct GatherArgs {
+    int NP;
+    long n, pos_stride;
+    const int* perm;           // internal -> input index, -1 for padding
+    const double *xyz_in, *chi_in, *hard_in;
+    double *x, *y, *z, *diag, *chi, *hard;
+};
+
+struct GemmArgs {
+    const double* A;           // m x K, column-major
+    const double* B;           // n x K, column-major
+    double* C;                 // m x n
+    long lda, ldb, ldc;
+    long strideA, strideB, strideC;  // per frame
+    int K;
+    int lower;                 // 1: skip tiles strictly above the diagonal of C
+    int subtract;              // 1: C -= A B^T ; 0: C = A B^T (C may alias A when the grid has one tile column)
+    const ScfState* state;     // nullable; frames with active == 0 are skipped
+};
+
+int assemble_smem_bytes(int table_bytes, int* table_smem_bytes);
+cudaError_t launch_assemble(const AssembleArgs& a, const PairTableView& view, const char* blob, int blob_bytes,
+                            int batch, cudaStream_t stream);
+cudaError_t launch_rhs_rows(double* A, long ld, long a_stride, int NP, const double* chi, const double* vext,
+                            long vec_stride, const uint8_t* type, int batch, cudaStream_t stream);
+cudaError_t launch_vext(const VextArgs& a, const PairTableView& view, const char* blob, int blob_bytes,
+                        cudaStream_t stream);
+cudaError_t launch_pair_list(long count, const double* dist, const int* ti, const int* tj,
+                             const PairTableView& view, double* out, cudaStream_t stream);
+cudaError_t launch_gather(const GatherArgs& g, int batch, cudaStream_t stream);
+cudaError_t launch_scatter_charges(int NP, const int* perm, const double* q, long q_stride, double* out, long n,
+                                   int batch, cudaStream_t stream);
+cudaError_t launch_export_matrix(int NP, long ld, const double* A, const int* perm, long n, double* out,
+                                 cudaStream_t stream);
+
+// ---- dense (kernels_dense.cu) ------------------------------------------------------------------------------
+cudaError_t launch_gemm_nt(const GemmArgs& g, int m_tiles, int n_tiles, int batch, cudaStream_t stream);
+// Cholesky of one 128 x 128 diagonal block in place (lower) + its inverse (dense 128 x 128, ld 128).
+cudaError_t launch_potrf_tile(double* A, long lda, long strideA, double* Linv, long strideLinv, ScfState* state,
+                              int batch, cudaStream_t stream);
+// copies the tiles on/below the diagonal of an (m_tiles x n_tiles) tile region
+cudaError_t launch_copy_lower_tiles(const double* src, long lds, long stride_src, double* dst, long ldd,
+                                    long stride_dst, int m_tiles, int n_tiles, const ScfState* state, int batch,
+                                    cudaStream_t stream);
+// A_ii = S0_ii + hardness_i * kHChargeFactor * clamp(q_i, -0.95, 0.95) for the real atoms of the hydrogen block
+cudaError_t launch_set_h_diagonal(double* A, long lda, long strideA, const double* S0, long ld0, long stride0,
+                                  const double* hard_h, const double* q_h, long q_stride, const uint8_t* type_h,
+                                  int nhp, const ScfState* state, int batch, cudaStream_t stream);
+// mu = (f1.fc - Q) / (f1.f1) from rows NP, NP+1; v = fc - mu f1
+cudaError_t launch_mu(const double* A, long lda, long strideA, int NP, double total_charge, double* v,
+                      long v_stride, ScfState* state, int batch, cudaStream_t stream);
+// one block-row step (block kb) of the backward substitution L^T x = v, in place in v
+cudaError_t launch_backsolve_step(const double* A, long lda, long strideA, const double* Linv, long strideLinv,
+                                  int NP, int kb, double* v, long v_stride, double* scratch, long scratch_stride,
+                                  unsigned* counters, const ScfState* state, int batch, cudaStream_t stream);
+int backsolve_max_ctas();
+// delta = max |x - q| over real atoms; q <- (1 - d) q + d x
+cudaError_t launch_scf_mix(const double* x, double* q, long stride, const uint8_t* type, int NP, ScfState* state,
+                           int batch, cudaStream_t stream);
+// convergence test + damping schedule (implementation.rs:316-338); damping_kind as in cheq_b200.h
+cudaError_t launch_scf_decide(ScfState* state, double tolerance, int damping_kind, int batch, int* active_count,
+                              cudaStream_t stream);
+cudaError_t launch_scf_init(ScfState* state, double damping, int batch, cudaStream_t stream);
+
+// ---- LU fallback (kernels_lu.cu) ------------------------------------------------------------------------------
+int lu_padded_size(int NP);
+// Builds the bordered matrix from the assembled lower triangle (A is left untouched), factors it with partial
+// pivoting, solves, and writes x (internal order) to v and the border unknown to state[0].mu.
+cudaError_t launch_lu_solve(const double* A, long ld, int NP, int nxp, int scf, double* F, const double* q,
+                            const double* hard, const uint8_t* type, double total_charge, int* ipiv, double* v,
+                            ScfState* state, unsigned long long* launches, cudaStream_t stream);
+
+}  // namespace cheq

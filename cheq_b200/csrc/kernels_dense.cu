@@ -1,0 +1,490 @@
+// Dense FP64 kernels of the QEq solve for sm_100a.
+//
+// Replaces `work_matrix.partial_piv_lu().solve(&rhs)` (/root/reference/src/solver/implementation.rs:574-576,
+// un-vendored crate faer) and the vector part of run_single_solve / run_scf_iterations (:557-603, :303-339).
+// The bordered system is solved by constraint elimination on a blocked Cholesky factorisation
+// (SURVEY.md App. E): the right-hand sides ride along as two extra rows of the trapezoid, so the forward
+// substitution is part of the factorisation.
+//
+// FP64 on Blackwell has no tcgen05 kind; the tensor path is mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).  The
+// GEMM below stages 128 x 16 operand slabs with cp.async (LDGSTS) into padded shared memory (row stride
+// 132 doubles -> conflict-free 16-byte fragment loads), 4 stages, 8 warps each owning a 64 x 32 accumulator
+// tile (64 fp64 registers per thread), 32 DMMAs per 6 LDS.128.
+#include <cuda_runtime.h>
+
+#include "device_types.h"
+#include "kernels.h"
+
+namespace cheq {
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------
+// GEMM  C (-)= A * B^T,  A: m x K, B: n x K, column-major, all dimensions multiples of 128 (K of 16)
+// ------------------------------------------------------------------------------------------------------------
+constexpr int BM = 128, BN = 128, BK = 16, LDT = 132, STAGES = 4;
+constexpr int kGemmThreads = 256;
+constexpr int kGemmSmem = STAGES * 2 * BK * LDT * (int)sizeof(double);  // 135168 B
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_nt_kernel(GemmArgs g) {
+    const int tile_m = blockIdx.x, tile_n = blockIdx.y, frame = blockIdx.z;
+    if (g.lower && tile_m < tile_n) return;
+    if (g.state && !g.state[frame].active) return;
+    extern __shared__ __align__(16) double smem[];
+    double* As = smem;                          // [STAGES][BK][LDT]
+    double* Bs = smem + STAGES * BK * LDT;      // [STAGES][BK][LDT]
+
+    const double* A = g.A + (long)frame * g.strideA + (long)tile_m * BM;
+    const double* B = g.B + (long)frame * g.strideB + (long)tile_n * BN;
+    double* C = g.C + (long)frame * g.strideC + (long)tile_m * BM + (long)tile_n * BN * g.ldc;
+
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int wm = warp & 1, wn = warp >> 1;   // 2 x 4 warps, warp tile 64 x 32
+    const int gq = lane >> 2, q = lane & 3;
+
+    auto load_stage = [&](int stage, int ktile) {
+        double* as = As + stage * BK * LDT;
+        double* bs = Bs + stage * BK * LDT;
+        const long k0 = (long)ktile * BK;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int c = t + i * kGemmThreads;   // 0..1023
+            const int kr = c >> 6, mc = c & 63;
+            cp_async16(as + kr * LDT + 2 * mc, A + 2 * mc + (k0 + kr) * g.lda);
+            cp_async16(bs + kr * LDT + 2 * mc, B + 2 * mc + (k0 + kr) * g.ldb);
+        }
+    };
+
+    double acc[4][2][2][2][2];  // [fm][row parity][fn][col parity][e]
+#pragma unroll
+    for (int i = 0; i < 64; ++i) ((double*)acc)[i] = 0.0;
+
+    const int kt = g.K / BK;
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < kt) load_stage(s, s);
+        cp_async_commit();
+    }
+
+    for (int it = 0; it < kt; ++it) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            const int nxt = it + STAGES - 1;
+            if (nxt < kt) load_stage(nxt % STAGES, nxt);
+            cp_async_commit();
+        }
+        const double* as = As + (it % STAGES) * BK * LDT + wm * 64 + 2 * gq;
+        const double* bs = Bs + (it % STAGES) * BK * LDT + wn * 32 + 2 * gq;
+#pragma unroll
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            double2 a[4], b[2];
+#pragma unroll
+            for (int fm = 0; fm < 4; ++fm) a[fm] = *(const double2*)(as + (kk * 4 + q) * LDT + fm * 16);
+#pragma unroll
+            for (int fn = 0; fn < 2; ++fn) b[fn] = *(const double2*)(bs + (kk * 4 + q) * LDT + fn * 16);
+#pragma unroll
+            for (int fm = 0; fm < 4; ++fm)
+#pragma unroll
+                for (int fn = 0; fn < 2; ++fn) {
+                    dmma884(acc[fm][0][fn][0][0], acc[fm][0][fn][0][1], a[fm].x, b[fn].x);
+                    dmma884(acc[fm][0][fn][1][0], acc[fm][0][fn][1][1], a[fm].x, b[fn].y);
+                    dmma884(acc[fm][1][fn][0][0], acc[fm][1][fn][0][1], a[fm].y, b[fn].x);
+                    dmma884(acc[fm][1][fn][1][0], acc[fm][1][fn][1][1], a[fm].y, b[fn].y);
+                }
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: thread owns rows (2 gq, 2 gq + 1) of each 16-row group and columns 4 q + 2 e + pc of each
+    // 16-column group
+#pragma unroll
+    for (int fm = 0; fm < 4; ++fm) {
+        const int row = wm * 64 + fm * 16 + 2 * gq;
+#pragma unroll
+        for (int fn = 0; fn < 2; ++fn)
+#pragma unroll
+            for (int pc = 0; pc < 2; ++pc)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int col = wn * 32 + fn * 16 + 4 * q + 2 * e + pc;
+                    double2* p = (double2*)(C + row + (long)col * g.ldc);
+                    double2 v = make_double2(acc[fm][0][fn][pc][e], acc[fm][1][fn][pc][e]);
+                    if (g.subtract) {
+                        double2 old = *p;
+                        v.x = old.x - v.x;
+                        v.y = old.y - v.y;
+                    }
+                    *p = v;
+                }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// 128 x 128 diagonal block: Cholesky (lower, in place) and the inverse of the factor, one CTA.
+// Shared array S[col * 128 + row]: the lower triangle holds A -> L, the strict upper triangle holds the strict
+// lower triangle of X = L^-1 transposed in place (X_ij, i > j, at S[i * 128 + j]); diag(X) in dinv.
+// Step k finalises column k of L, then applies the rank-1 updates of both the trailing matrix and of X.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kPotrfThreads = 256;
+constexpr int kPotrfSmem = (kTile * kTile + kTile) * (int)sizeof(double);
+
+__global__ void __launch_bounds__(kPotrfThreads)
+potrf_tile_kernel(double* A_, long lda, long strideA, double* Linv_, long strideLinv, ScfState* state) {
+    const int frame = blockIdx.z;
+    if (state && !state[frame].active) return;
+    extern __shared__ __align__(16) double S[];
+    double* dinv = S + kTile * kTile;
+    double* A = A_ + (long)frame * strideA;
+    double* Linv = Linv_ + (long)frame * strideLinv;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+
+    for (int idx = t; idx < kTile * kTile; idx += kPotrfThreads) {
+        const int i = idx & (kTile - 1), j = idx >> 7;
+        S[idx] = (i >= j) ? A[i + (long)j * lda] : 0.0;
+    }
+    __syncthreads();
+
+    for (int k = 0; k < kTile; ++k) {
+        const double d = S[k * kTile + k];
+        const bool bad = !(d > 0.0) || !(d < 1.7e308);
+        if (bad && t == 0 && state) atomicExch(&state[frame].info, k + 1);
+        const double l = bad ? 1.0 : sqrt(d);
+        const double inv = 1.0 / l;
+        __syncthreads();  // everybody has read d
+        if (t >= k && t < kTile) S[k * kTile + t] = (t == k) ? l : S[k * kTile + t] * inv;   // column k of L
+        if (t > kTile && t - kTile <= k) {                                                  // row k of X
+            const int j = t - kTile - 1;   // 0..k-1
+            if (j < k) S[k * kTile + j] *= inv;
+        }
+        if (t == kTile) dinv[k] = inv;
+        __syncthreads();
+        // trailing update of A: S[j][i] -= L_ik L_jk, k < j <= i
+        for (int j = k + 1 + warp; j < kTile; j += kPotrfThreads / 32) {
+            const double ljk = S[k * kTile + j];
+            for (int i = j + lane; i < kTile; i += 32) S[j * kTile + i] -= S[k * kTile + i] * ljk;
+        }
+        // update of X: X_ij -= L_ik X_kj for i > k, j <= k   (X_kk = dinv[k], X_ik starts at 0)
+        const int w = k + 1;   // row k of X has k + 1 entries
+        for (int e = t; e < (kTile - 1 - k) * w; e += kPotrfThreads) {
+            const int i = k + 1 + e / w, j = e - (e / w) * w;
+            const double xkj = (j == k) ? inv : S[k * kTile + j];
+            S[i * kTile + j] -= S[k * kTile + i] * xkj;
+        }
+        // no barrier needed here: the next iteration's first barrier orders these writes before its reads of
+        // column k+1 / row k+1?  Not so -- d is read before that barrier, hence:
+        __syncthreads();
+    }
+
+    for (int idx = t; idx < kTile * kTile; idx += kPotrfThreads) {
+        const int i = idx & (kTile - 1), j = idx >> 7;
+        if (i >= j) A[i + (long)j * lda] = S[idx];
+        double x = 0.0;
+        if (i > j) x = S[i * kTile + j];
+        else if (i == j) x = dinv[i];
+        Linv[idx] = x;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+copy_lower_tiles_kernel(const double* src, long lds, long stride_src, double* dst, long ldd, long stride_dst,
+                        const ScfState* state) {
+    const int ti = blockIdx.x, tj = blockIdx.y, frame = blockIdx.z;
+    if (ti < tj) return;
+    if (state && !state[frame].active) return;
+    const double* s = src + (long)frame * stride_src + (long)ti * kTile + (long)tj * kTile * lds;
+    double* d = dst + (long)frame * stride_dst + (long)ti * kTile + (long)tj * kTile * ldd;
+    for (int idx = threadIdx.x; idx < kTile * kTile / 2; idx += 256) {
+        const int r2 = idx & 63, c = idx >> 6;
+        *(double2*)(d + 2 * r2 + (long)c * ldd) = *(const double2*)(s + 2 * r2 + (long)c * lds);
+    }
+}
+
+__global__ void set_h_diagonal_kernel(double* A, long lda, long strideA, const double* S0, long ld0,
+                                      long stride0, const double* hard_h, const double* q_h, long q_stride,
+                                      const uint8_t* type_h, int nhp, const ScfState* state) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int frame = blockIdx.z;
+    if (i >= nhp) return;
+    if (state && !state[frame].active) return;
+    if (type_h[i] == kPadType) return;
+    // implementation.rs:567-572: hardness * (1 + clamp(q, -0.95, 0.95) * H_CHARGE_DEPENDENCE_FACTOR)
+    const double q = q_h[(long)frame * q_stride + i];
+    const double qc = fmin(fmax(q, -0.95), 0.95);
+    const double base = S0[(long)frame * stride0 + (long)i + (long)i * ld0];
+    A[(long)frame * strideA + (long)i + (long)i * lda] = base + hard_h[i] * (qc * kHChargeFactor);
+}
+
+// mu and the combined right-hand side.  One CTA per frame; fixed summation order.
+__global__ void __launch_bounds__(1024)
+mu_kernel(const double* A_, long lda, long strideA, int NP, double total_charge, double* v_, long v_stride,
+          ScfState* state) {
+    const int frame = blockIdx.z;
+    if (!state[frame].active) return;
+    const double* fc = A_ + (long)frame * strideA + NP;   // row NP
+    const double* f1 = fc + 1;                            // row NP + 1
+    double* v = v_ + (long)frame * v_stride;
+    __shared__ double s11[32], s1c[32];
+    __shared__ double mu_s;
+    double a11 = 0.0, a1c = 0.0;
+    for (int j = threadIdx.x; j < NP; j += 1024) {
+        const double x1 = f1[(long)j * lda], xc = fc[(long)j * lda];
+        a11 = fma(x1, x1, a11);
+        a1c = fma(x1, xc, a1c);
+    }
+    for (int off = 16; off > 0; off >>= 1) {
+        a11 += __shfl_xor_sync(0xffffffffu, a11, off);
+        a1c += __shfl_xor_sync(0xffffffffu, a1c, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        s11[threadIdx.x >> 5] = a11;
+        s1c[threadIdx.x >> 5] = a1c;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t11 = 0.0, t1c = 0.0;
+        for (int w = 0; w < 32; ++w) {
+            t11 += s11[w];
+            t1c += s1c[w];
+        }
+        const double mu = (t1c - total_charge) / t11;
+        mu_s = mu;
+        state[frame].mu = mu;
+    }
+    __syncthreads();
+    const double mu = mu_s;
+    for (int j = threadIdx.x; j < NP; j += 1024) v[j] = fc[(long)j * lda] - mu * f1[(long)j * lda];
+}
+
+// Backward substitution, block row kb:  x_kb = Linv_kb^T (v_kb - L[rows below, kb cols]^T x[rows below]).
+constexpr int kBackMaxCtas = 32;
+__global__ void __launch_bounds__(256)
+backsolve_step_kernel(const double* A_, long lda, long strideA, const double* Linv_, long strideLinv, int NP,
+                      int kb, double* v_, long v_stride, double* scratch_, long scratch_stride,
+                      unsigned* counters, const ScfState* state) {
+    const int frame = blockIdx.z;
+    if (state && !state[frame].active) return;
+    const double* A = A_ + (long)frame * strideA;
+    const double* Linv = Linv_ + (long)frame * strideLinv + (long)kb * kTile * kTile;
+    double* v = v_ + (long)frame * v_stride;
+    double* scratch = scratch_ + (long)frame * scratch_stride;
+    const int G = gridDim.x, c = blockIdx.x;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int r_lo = (kb + 1) * kTile;
+    const int rows = NP - r_lo;
+    int chunk = (rows + G - 1) / G;
+    chunk = (chunk + 31) & ~31;
+    const int r0 = r_lo + c * chunk;
+    const int r1 = min(NP, r0 + chunk);
+
+    for (int col = warp; col < kTile; col += 8) {
+        const double* Lc = A + (long)(kb * kTile + col) * lda;
+        double s = 0.0;
+        for (int r = r0 + lane; r < r1; r += 32) s = fma(Lc[r], v[r], s);
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) scratch[c * kTile + col] = s;
+    }
+    __shared__ bool is_last;
+    __shared__ double tv[kTile];
+    __threadfence();
+    __syncthreads();
+    if (t == 0) {
+        const unsigned prev = atomicAdd(&counters[frame], 1u);
+        is_last = (prev == (unsigned)(G - 1));
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (t < kTile) {
+        double s = 0.0;
+        for (int cc = 0; cc < G; ++cc) s += __ldcg(&scratch[cc * kTile + t]);
+        tv[t] = v[kb * kTile + t] - s;
+    }
+    __syncthreads();
+    for (int i = warp; i < kTile; i += 8) {
+        // x_i = sum_{j >= i} Linv[j, i] tv[j]
+        const double* Xc = Linv + (long)i * kTile;
+        double s = 0.0;
+        for (int j = i + lane; j < kTile; j += 32) s = fma(Xc[j], tv[j], s);
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if (lane == 0) v[kb * kTile + i] = s;
+    }
+    if (t == 0) counters[frame] = 0u;
+}
+
+__global__ void __launch_bounds__(256)
+scf_mix_kernel(const double* x_, double* q_, long stride, const uint8_t* type, int NP, ScfState* state) {
+    const int frame = blockIdx.z;
+    if (!state[frame].active) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const double d = state[frame].damping;
+    double diff = 0.0;
+    if (i < NP && type[i] != kPadType) {
+        const double xn = x_[(long)frame * stride + i];
+        const double qo = q_[(long)frame * stride + i];
+        diff = fabs(xn - qo);                                   // implementation.rs:589-594
+        q_[(long)frame * stride + i] = (1.0 - d) * qo + d * xn;  // implementation.rs:596-598
+    }
+    for (int off = 16; off > 0; off >>= 1) diff = fmax(diff, __shfl_xor_sync(0xffffffffu, diff, off));
+    __shared__ double wmax[8];
+    if ((threadIdx.x & 31) == 0) wmax[threadIdx.x >> 5] = diff;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double m = 0.0;
+        for (int w = 0; w < 8; ++w) m = fmax(m, wmax[w]);
+        atomicMax(&state[frame].delta_bits, (unsigned long long)__double_as_longlong(m));
+    }
+}
+
+__global__ void scf_decide_kernel(ScfState* state, double tolerance, int damping_kind, int batch,
+                                  int* active_count) {
+    const int frame = blockIdx.x * blockDim.x + threadIdx.x;
+    if (frame >= batch) return;
+    ScfState& s = state[frame];
+    if (!s.active) return;
+    const double delta = __longlong_as_double((long long)s.delta_bits);
+    s.delta_bits = 0ull;
+    s.delta = delta;
+    s.iteration += 1;
+    if (s.info != 0) {
+        s.active = 0;
+        return;
+    }
+    if (delta < tolerance) {            // implementation.rs:318
+        s.converged = 1;
+        s.active = 0;
+        return;
+    }
+    if (damping_kind == 2) {            // implementation.rs:326-336
+        double d = s.damping;
+        if (delta > s.prev_delta) d *= 0.5;
+        else if (delta < s.prev_delta * 0.9) d = fmin(d * 1.1, 1.0);
+        if (d < 0.001) d = 0.001;
+        s.damping = d;
+    }
+    s.prev_delta = delta;
+    atomicAdd(active_count, 1);
+}
+
+__global__ void scf_init_kernel(ScfState* state, double damping, int batch) {
+    const int frame = blockIdx.x * blockDim.x + threadIdx.x;
+    if (frame >= batch) return;
+    ScfState s;
+    s.damping = damping;
+    s.prev_delta = 1.7976931348623157e308;   // f64::MAX, implementation.rs:295
+    s.delta = 0.0;
+    s.mu = 0.0;
+    s.delta_bits = 0ull;
+    s.iteration = 0;
+    s.converged = 0;
+    s.info = 0;
+    s.active = 1;
+    state[frame] = s;
+}
+
+}  // namespace
+
+cudaError_t launch_gemm_nt(const GemmArgs& g, int m_tiles, int n_tiles, int batch, cudaStream_t stream) {
+    if (m_tiles <= 0 || n_tiles <= 0) return cudaSuccess;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dim3 grid(m_tiles, n_tiles, batch);
+    gemm_nt_kernel<<<grid, kGemmThreads, kGemmSmem, stream>>>(g);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_potrf_tile(double* A, long lda, long strideA, double* Linv, long strideLinv, ScfState* state,
+                              int batch, cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e =
+            cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPotrfSmem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    dim3 grid(1, 1, batch);
+    potrf_tile_kernel<<<grid, kPotrfThreads, kPotrfSmem, stream>>>(A, lda, strideA, Linv, strideLinv, state);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_copy_lower_tiles(const double* src, long lds, long stride_src, double* dst, long ldd,
+                                    long stride_dst, int m_tiles, int n_tiles, const ScfState* state, int batch,
+                                    cudaStream_t stream) {
+    if (m_tiles <= 0 || n_tiles <= 0) return cudaSuccess;
+    dim3 grid(m_tiles, n_tiles, batch);
+    copy_lower_tiles_kernel<<<grid, 256, 0, stream>>>(src, lds, stride_src, dst, ldd, stride_dst, state);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_set_h_diagonal(double* A, long lda, long strideA, const double* S0, long ld0, long stride0,
+                                  const double* hard_h, const double* q_h, long q_stride, const uint8_t* type_h,
+                                  int nhp, const ScfState* state, int batch, cudaStream_t stream) {
+    if (nhp <= 0) return cudaSuccess;
+    dim3 grid((nhp + 255) / 256, 1, batch);
+    set_h_diagonal_kernel<<<grid, 256, 0, stream>>>(A, lda, strideA, S0, ld0, stride0, hard_h, q_h, q_stride,
+                                                    type_h, nhp, state);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mu(const double* A, long lda, long strideA, int NP, double total_charge, double* v,
+                      long v_stride, ScfState* state, int batch, cudaStream_t stream) {
+    dim3 grid(1, 1, batch);
+    mu_kernel<<<grid, 1024, 0, stream>>>(A, lda, strideA, NP, total_charge, v, v_stride, state);
+    return cudaGetLastError();
+}
+
+int backsolve_max_ctas() { return kBackMaxCtas; }
+
+cudaError_t launch_backsolve_step(const double* A, long lda, long strideA, const double* Linv, long strideLinv,
+                                  int NP, int kb, double* v, long v_stride, double* scratch, long scratch_stride,
+                                  unsigned* counters, const ScfState* state, int batch, cudaStream_t stream) {
+    const int rows = NP - (kb + 1) * kTile;
+    int G = (rows + 511) / 512;
+    if (G < 1) G = 1;
+    if (G > kBackMaxCtas) G = kBackMaxCtas;
+    dim3 grid(G, 1, batch);
+    backsolve_step_kernel<<<grid, 256, 0, stream>>>(A, lda, strideA, Linv, strideLinv, NP, kb, v, v_stride,
+                                                    scratch, scratch_stride, counters, state);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scf_mix(const double* x, double* q, long stride, const uint8_t* type, int NP, ScfState* state,
+                           int batch, cudaStream_t stream) {
+    dim3 grid((NP + 255) / 256, 1, batch);
+    scf_mix_kernel<<<grid, 256, 0, stream>>>(x, q, stride, type, NP, state);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scf_decide(ScfState* state, double tolerance, int damping_kind, int batch, int* active_count,
+                              cudaStream_t stream) {
+    scf_decide_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(state, tolerance, damping_kind, batch,
+                                                                active_count);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scf_init(ScfState* state, double damping, int batch, cudaStream_t stream) {
+    scf_init_kernel<<<(batch + 127) / 128, 128, 0, stream>>>(state, damping, batch);
+    return cudaGetLastError();
+}
+
+}  // namespace cheq

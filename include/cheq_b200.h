@@ -1,0 +1,170 @@
+/*
+ * cheq_b200.h -- C ABI of the B200-native QEq engine (drop-in for the hot path of caltechmsc/cheq).
+ *
+ * The reference is a pure-Rust crate with no FFI layer; its boundary is the Rust public API
+ * (/root/reference/src/lib.rs:98-104).  This header is what a `cheq-b200-sys` crate binds so that
+ * `QEqSolver::solve` / `solve_in_field` (src/solver/implementation.rs:174-188, 239-266) can hand the
+ * whole numerical path -- `build_invariant_system` (:454-554), `compute_external_potential` (:369-447),
+ * `run_scf_iterations` (:273-345) and `run_single_solve` (:557-603) -- to the GPU.  The seam sits after
+ * `fetch_element_data` (:348-362): the caller resolves atomic numbers to per-atom parameters
+ * (ParameterNotFound stays on the host side) and passes plain arrays.
+ *
+ * Conventions
+ *   - All pointers are caller-owned.  `cheq_solve*` takes HOST pointers; `cheq_solve_device` takes DEVICE
+ *     pointers for the per-atom arrays (inputs already resident in HBM) and host pointers for scalars.
+ *   - Positions and radii in Angstrom, energies in eV, charges in e (cheq's units, constants.rs:13,22).
+ *   - Every function returns a status code and never unwinds.  `cheq_last_error` gives the text.
+ *   - A context owns one CUDA stream and a grow-only device workspace; calls on one context are serialised
+ *     by an internal mutex, distinct contexts are independent (QEqSolver is Send + Sync in the reference).
+ *   - There is no CPU fallback: without a CUDA device `cheq_ctx_create` fails with CHEQ_ERR_CUDA.
+ */
+#ifndef CHEQ_B200_H
+#define CHEQ_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* Status codes.  1..4 mirror CheqError (src/error.rs:18-68). */
+#define CHEQ_OK 0
+#define CHEQ_ERR_NO_ATOMS 1            /* CheqError::NoAtoms           (implementation.rs:180-182, 250-252) */
+#define CHEQ_ERR_PARAMETER_NOT_FOUND 2 /* CheqError::ParameterNotFound (raised by the host shim, :348-362, :378-387) */
+#define CHEQ_ERR_NOT_CONVERGED 3       /* CheqError::NotConverged      (implementation.rs:341-344) */
+#define CHEQ_ERR_LINALG 4              /* CheqError::LinalgError       (implementation.rs:578-585) */
+#define CHEQ_ERR_CUDA 5                /* CUDA runtime failure (no reference equivalent) */
+#define CHEQ_ERR_INVALID_ARGUMENT 6
+#define CHEQ_ERR_OUT_OF_MEMORY 7
+
+#define CHEQ_BASIS_GTO 0 /* BasisType::Gto (options.rs:9-22) */
+#define CHEQ_BASIS_STO 1 /* BasisType::Sto, the default */
+
+#define CHEQ_DAMPING_NONE 0  /* DampingStrategy::None        (options.rs:26-45) */
+#define CHEQ_DAMPING_FIXED 1 /* DampingStrategy::Fixed(d)  */
+#define CHEQ_DAMPING_AUTO 2  /* DampingStrategy::Auto { initial } */
+
+typedef struct cheq_ctx cheq_ctx;
+
+/* SolverOptions (options.rs:53-100), passed by value semantics. */
+typedef struct cheq_options {
+    double tolerance;        /* max-abs charge change accepted as converged; default 1e-6 */
+    double lambda_scale;     /* Slater exponent scale lambda; default 0.5 */
+    double damping_value;    /* Fixed(d) or Auto{initial}; ignored for None; default 0.4 */
+    uint32_t max_iterations; /* default 2000 (the reference CLI uses 100) */
+    uint8_t hydrogen_scf;    /* default 1 */
+    uint8_t basis;           /* CHEQ_BASIS_*; default STO */
+    uint8_t damping_kind;    /* CHEQ_DAMPING_*; default AUTO */
+    uint8_t reserved;
+} cheq_options;
+
+/* ExternalPotential (types.rs:84-97, 136-148) with point-charge elements already resolved. */
+typedef struct cheq_external {
+    uint64_t num_point_charges;
+    const double* xyz;     /* 3 * m, AoS */
+    const double* charge;  /* m */
+    const double* radius;  /* m, covalent radius of each point charge's element */
+    const uint8_t* n;      /* m, principal quantum number of each point charge's element */
+    double field[3];       /* uniform field, V/Angstrom */
+} cheq_external;
+
+/* Per-call measurements (device times from CUDA events on the context's stream). */
+typedef struct cheq_stats {
+    double ms_total;         /* whole call, host clock */
+    double ms_host_prepare;  /* typing, ordering, table construction */
+    double ms_h2d;           /* input upload (0 for cheq_solve_device) */
+    double ms_assemble;      /* v_ext + matrix assembly kernels */
+    double ms_factor_once;   /* geometry-invariant part of the factorisation */
+    double ms_scf;           /* all SCF iterations (refactorisation of the hydrogen block + solves) */
+    double ms_d2h;           /* result download */
+    uint64_t kernel_launches;
+    uint64_t n_atoms, n_hydrogen, n_padded;
+    uint32_t iterations;
+    uint32_t pair_types;
+    double flops_factor;     /* LAPACK-count flops of the factorisation work actually performed */
+    double bytes_assemble;   /* algorithmic bytes of the assembly: 8 * N (N + 1) / 2 */
+    uint64_t lu_fallback_frames; /* frames re-solved with the pivoted-LU path (matrix not positive definite) */
+} cheq_stats;
+
+int32_t cheq_ctx_create(int32_t device, cheq_ctx** out);
+void cheq_ctx_destroy(cheq_ctx* ctx);
+const char* cheq_last_error(const cheq_ctx* ctx);
+void cheq_options_default(cheq_options* opt);
+int32_t cheq_get_stats(const cheq_ctx* ctx, cheq_stats* out);
+/* The context's CUDA stream as a cudaStream_t cast to void* (for callers that time with events). */
+void* cheq_ctx_stream(const cheq_ctx* ctx);
+
+/*
+ * QEqSolver::solve / solve_in_field after element lookup.  `external` may be NULL or empty
+ * (types.rs:281-286) for a vacuum solve.  On CHEQ_OK and on CHEQ_ERR_NOT_CONVERGED the outputs hold the
+ * last iterate (the reference returns only max_iterations and delta on NotConverged).
+ *   charges_out[n]      CalculationResult::charges, input order
+ *   potential_out       CalculationResult::equilibrated_potential (the bordered system's last unknown)
+ *   iterations_out      CalculationResult::iterations (1 when the SCF is skipped)
+ *   delta_out           last max-abs charge change (NotConverged::delta)
+ */
+int32_t cheq_solve(cheq_ctx* ctx, uint64_t n_atoms, const double* xyz, const double* chi,
+                   const double* hardness, const double* radius, const uint8_t* n_quantum,
+                   double total_charge, const cheq_options* options, const cheq_external* external,
+                   double* charges_out, double* potential_out, uint32_t* iterations_out,
+                   double* delta_out);
+
+/* Same, with xyz/chi/hardness/radius/n_quantum/charges_out (and the external arrays) in DEVICE memory. */
+int32_t cheq_solve_device(cheq_ctx* ctx, uint64_t n_atoms, const double* d_xyz, const double* d_chi,
+                          const double* d_hardness, const double* d_radius, const uint8_t* d_n_quantum,
+                          double total_charge, const cheq_options* options, const cheq_external* d_external,
+                          double* d_charges_out, double* potential_out, uint32_t* iterations_out,
+                          double* delta_out);
+
+/*
+ * Batched frames of ONE topology (an MD trajectory): per-atom parameters are shared, coordinates differ.
+ *   xyz            n_frames * n_atoms * 3
+ *   charges_out    n_frames * n_atoms
+ *   potential_out, iterations_out, delta_out, status_out   n_frames each (status per frame, CHEQ_* codes)
+ * Returns CHEQ_OK if the batch ran; per-frame convergence failures are reported in status_out.
+ */
+int32_t cheq_solve_batch(cheq_ctx* ctx, uint64_t n_frames, uint64_t n_atoms, const double* xyz,
+                         const double* chi, const double* hardness, const double* radius,
+                         const uint8_t* n_quantum, double total_charge, const cheq_options* options,
+                         double* charges_out, double* potential_out, uint32_t* iterations_out,
+                         double* delta_out, int32_t* status_out);
+
+/* ---- component entry points (used by the parity tests; same kernels as cheq_solve) -------------- */
+
+/* shielding::{sto,gto}::calculate_integral (sto.rs:27-39, gto.rs:28-43) * HARTREE_TO_EV for `count` independent
+ * pairs: distance in Angstrom, radii in Angstrom; out_ev[count].  Host pointers. */
+int32_t cheq_pair_integrals(cheq_ctx* ctx, uint64_t count, const double* distance, const uint8_t* n1,
+                            const double* radius1, const uint8_t* n2, const double* radius2,
+                            double lambda_scale, uint8_t basis, double* out_ev);
+
+/* build_invariant_system's matrix without the border (implementation.rs:468-536): n x n, column-major,
+ * diagonal = hardness, off-diagonal = J_eV, both triangles filled, input atom order.  Host pointers. */
+int32_t cheq_assemble_matrix(cheq_ctx* ctx, uint64_t n_atoms, const double* xyz, const double* hardness,
+                             const double* radius, const uint8_t* n_quantum, double lambda_scale,
+                             uint8_t basis, double* matrix_out);
+
+/* compute_external_potential (implementation.rs:369-447): v_out[n].  Host pointers. */
+int32_t cheq_external_potential(cheq_ctx* ctx, uint64_t n_atoms, const double* xyz, const double* radius,
+                                const uint8_t* n_quantum, const cheq_external* external,
+                                double lambda_scale, uint8_t basis, double* v_out);
+
+/* Dense kernels, exposed for unit tests.  All matrices column-major in HOST memory.
+ *   cheq_dbg_cholesky_solve: solves A x = b for SPD A (n x n, lower triangle read) with the blocked
+ *     tensor-core factorisation used by cheq_solve; nrhs <= 2.  Returns CHEQ_ERR_LINALG if not SPD.
+ *   cheq_dbg_gemm_nt: C (m x n) = beta * C - ... : C <- C - A B^T when subtract != 0, else C <- A B^T;
+ *     m, n, k multiples of 128. */
+int32_t cheq_dbg_cholesky_solve(cheq_ctx* ctx, uint64_t n, const double* a, uint64_t nrhs, const double* b,
+                                double* x_out, double* l_out /* nullable, n x n */);
+int32_t cheq_dbg_gemm_nt(cheq_ctx* ctx, uint64_t m, uint64_t n, uint64_t k, const double* a,
+                         const double* b, double* c, int32_t subtract);
+
+/* Host-only: evaluates the STO pair table (built exactly as for the device) in fp64 on the CPU.  Used to
+ * test the table construction without a GPU; not a solve path.  Distance in bohr, result in Hartree. */
+double cheq_host_sto_table_eval(int32_t n1, double zeta1, int32_t n2, double zeta2, double distance_bohr,
+                                int32_t* kind_out, int32_t* terms_out, int32_t* coefs_out,
+                                double* max_abs_err_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHEQ_B200_H */

@@ -1,0 +1,364 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the golden fixtures.  Needs a B200.
+
+Tolerances (BASELINE.json north_star): 1e-8 e per atomic charge, 1e-8 eV in the equilibrated potential,
+identical SCF iteration counts; pair integrals and matrix entries are held to 1e-13 relative.
+"""
+import ctypes as C
+import math
+
+import mpmath as mp
+import numpy as np
+import pytest
+
+import cheq_b200
+from cheq_b200 import (Atom, BasisType, DampingStrategy, ExternalPotential, PointCharge, QEqSolver, SolverOptions,
+                       _ffi, get_default_parameters, workloads)
+from conftest import rg_cases
+
+pytestmark = pytest.mark.gpu
+
+BOHR = 0.529177210903
+EV = 27.211386245988
+Q_TOL = 1e-8
+MU_TOL = 1e-8
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def gpu_pair_integrals(ctx, dist_A, n1, r1, n2, r2, lam, basis):
+    dist_A = np.ascontiguousarray(dist_A, dtype=np.float64)
+    n1 = np.ascontiguousarray(n1, dtype=np.uint8)
+    n2 = np.ascontiguousarray(n2, dtype=np.uint8)
+    r1 = np.ascontiguousarray(r1, dtype=np.float64)
+    r2 = np.ascontiguousarray(r2, dtype=np.float64)
+    out = np.empty(len(dist_A))
+    rc = ctx._lib.cheq_pair_integrals(ctx.handle, len(dist_A), _ptr(dist_A), _ptr(n1), _ptr(r1), _ptr(n2), _ptr(r2),
+                                      lam, basis, _ptr(out))
+    assert rc == 0, ctx.last_error()
+    return out
+
+
+def solver(ctx, **kw):
+    return QEqSolver(get_default_parameters(), SolverOptions(**kw), ctx)
+
+
+def atoms_of(Z, xyz):
+    return [Atom(int(z), [float(c) for c in p]) for z, p in zip(Z, xyz)]
+
+
+def oracle_opts(oracle, o: SolverOptions):
+    return oracle.Options(tolerance=o.tolerance, max_iterations=o.max_iterations, lambda_scale=o.lambda_scale,
+                          hydrogen_scf=o.hydrogen_scf, basis=o.basis_type.value,
+                          damping=(o.damping.kind, o.damping.value))
+
+
+def assert_parity(res, ref):
+    assert res.iterations == ref.iterations, (res.iterations, ref.iterations)
+    dq = float(np.max(np.abs(np.array(res.charges) - ref.charges)))
+    dmu = abs(res.equilibrated_potential - ref.equilibrated_potential)
+    assert dq <= Q_TOL, dq
+    assert dmu <= MU_TOL, dmu
+    return dq, dmu
+
+
+# ---- pair integrals -------------------------------------------------------------------------------------------
+def test_pair_integrals_sto_vs_definition(gpu_ctx, sto_truth):
+    rows = [r for r in sto_truth["rows"] if r["z1"] != 0]      # element pairs of the default table
+    P = get_default_parameters().elements
+    d = np.array([float.fromhex(r["R_bohr"]) * BOHR for r in rows])
+    n1 = np.array([r["n1"] for r in rows]); n2 = np.array([r["n2"] for r in rows])
+    r1 = np.array([P[r["z1"]].radius for r in rows]); r2 = np.array([P[r["z2"]].radius for r in rows])
+    out = gpu_pair_integrals(gpu_ctx, d, n1, r1, n2, r2, sto_truth["lambda"], 1)
+    for r, v in zip(rows, out):
+        t = mp.mpf(r["J_hartree"]) * mp.mpf(EV)
+        R = float.fromhex(r["R_bohr"])
+        rel = float(abs((mp.mpf(float(v)) - t) / t))
+        assert rel < (1e-13 if R >= 0.5 else 1e-12), (r, v, rel)
+
+
+def test_pair_integrals_vs_oracle(gpu_ctx, oracle):
+    P = get_default_parameters().elements
+    rng = np.random.default_rng(7)
+    zs = [1, 2, 3, 6, 7, 8, 9, 11, 14, 15, 17, 19, 24, 25, 26, 29, 35, 37, 53, 55, 5, 23, 27, 42, 79, 92]
+    pairs = [(a, b) for a in zs for b in zs]
+    idx = rng.choice(len(pairs), size=400)
+    z1 = np.array([pairs[i][0] for i in idx]); z2 = np.array([pairs[i][1] for i in idx])
+    d = rng.uniform(0.5, 14.0, size=len(idx))
+    d[:20] = rng.uniform(20.0, 200.0, size=20)
+    n1 = np.array([P[z].principal_quantum_number for z in z1]); n2 = np.array([P[z].principal_quantum_number for z in z2])
+    r1 = np.array([P[z].radius for z in z1]); r2 = np.array([P[z].radius for z in z2])
+    for basis, lam in ((1, 0.5), (0, 0.5), (1, 0.4913), (0, 0.4913)):
+        out = gpu_pair_integrals(gpu_ctx, d, n1, r1, n2, r2, lam, basis)
+        f = oracle.sto_integral if basis == 1 else oracle.gto_integral
+        ref = np.array([f(d[k] / BOHR, int(n1[k]), r1[k] / BOHR, int(n2[k]), r2[k] / BOHR, lam) * EV
+                        for k in range(len(d))])
+        rel = np.max(np.abs(out - ref) / np.abs(ref))
+        assert rel < 1e-13, (basis, lam, rel)
+    # GTO known answers (gto.rs:182-197)
+    out = gpu_pair_integrals(gpu_ctx, [0.74, 1.128], [1, 2], [0.371, 0.759], [1, 2], [0.371, 0.669], 0.4913, 0)
+    assert abs(out[0] - 14.02504752) < 1e-8 and abs(out[1] - 5.837573337) < 1e-8
+    # R -> 0 limits are finite and continuous (sto.rs:84-94, gto.rs:154-166)
+    for basis in (0, 1):
+        o = gpu_pair_integrals(gpu_ctx, [0.0, 1e-10], [1, 1], [0.371, 0.371], [1, 1], [0.371, 0.371], 0.5, basis)
+        assert np.all(np.isfinite(o)) and abs(o[0] - o[1]) < 1e-6
+
+
+# ---- dense kernels ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("m,n,k", [(128, 128, 128), (256, 384, 256), (640, 128, 1152)])
+def test_gemm_nt_dmma(gpu_ctx, m, n, k):
+    rng = np.random.default_rng(m + n + k)
+    A = np.asfortranarray(rng.normal(size=(m, k)))
+    B = np.asfortranarray(rng.normal(size=(n, k)))
+    C0 = np.asfortranarray(rng.normal(size=(m, n)))
+    for sub in (1, 0):
+        Cg = C0.copy(order="F")
+        rc = gpu_ctx._lib.cheq_dbg_gemm_nt(gpu_ctx.handle, m, n, k, _ptr(A), _ptr(B), _ptr(Cg), sub)
+        assert rc == 0, gpu_ctx.last_error()
+        ref = C0 - A @ B.T if sub else A @ B.T
+        assert np.max(np.abs(Cg - ref)) < 1e-11 * math.sqrt(k)
+
+
+@pytest.mark.parametrize("n", [5, 128, 200, 515, 1300])
+def test_cholesky_solve(gpu_ctx, n):
+    rng = np.random.default_rng(n)
+    G = rng.normal(size=(n, n))
+    A = np.asfortranarray(G @ G.T / n + np.eye(n) * 2.0)
+    b = np.asfortranarray(rng.normal(size=(n, 2)))
+    x = np.empty((n, 2), order="F")
+    L = np.empty((n, n), order="F")
+    rc = gpu_ctx._lib.cheq_dbg_cholesky_solve(gpu_ctx.handle, n, _ptr(A), 2, _ptr(b), _ptr(x), _ptr(L))
+    assert rc == 0, gpu_ctx.last_error()
+    assert np.max(np.abs(L - np.linalg.cholesky(A))) < 1e-12
+    assert np.max(np.abs(x - np.linalg.solve(A, b))) < 1e-11
+    # an indefinite matrix is reported, not silently factored
+    A[0, 0] = -1.0
+    rc = gpu_ctx._lib.cheq_dbg_cholesky_solve(gpu_ctx.handle, n, _ptr(A), 2, _ptr(b), _ptr(x), None)
+    assert rc == _ffi.LINALG
+
+
+# ---- assembly -------------------------------------------------------------------------------------------------
+def _assemble(ctx, Z, xyz, lam, basis):
+    chi, hard, rad, nq = workloads.gather_parameters(Z, get_default_parameters())
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    n = len(Z)
+    M = np.empty((n, n), order="F")
+    rc = ctx._lib.cheq_assemble_matrix(ctx.handle, n, _ptr(xyz), _ptr(hard), _ptr(rad), _ptr(nq), lam, basis, _ptr(M))
+    assert rc == 0, ctx.last_error()
+    return M
+
+
+@pytest.mark.parametrize("basis", [1, 0])
+def test_assembled_matrix_vs_oracle(gpu_ctx, oracle, basis):
+    cases = [workloads.water_cluster(27), workloads.organic_chain(300),
+             ([3, 9, 11, 17, 55, 53, 26, 29, 1, 2, 79, 92, 14, 15],
+              np.random.default_rng(3).uniform(0, 6, size=(14, 3)))]
+    P = oracle.default_parameters()
+    for Z, xyz in cases:
+        M = _assemble(gpu_ctx, Z, xyz, 0.5, basis)
+        chi, hard, rad, nq = oracle.gather(Z, P)
+        ref, _, _ = oracle.build_system(xyz, chi, hard, rad, nq, 0.0, None, oracle.Options(basis=basis))
+        n = len(Z)
+        ref = ref[:n, :n]
+        assert np.array_equal(M, M.T)
+        assert np.max(np.abs(M - ref) / np.abs(ref)) < 1e-13
+
+
+def test_external_potential_vs_oracle(gpu_ctx, oracle):
+    Z, xyz = workloads.water_cluster(64)
+    rng = np.random.default_rng(11)
+    m = 500
+    pcZ = rng.choice([1, 6, 7, 8, 11, 17], size=m)
+    pc_xyz = rng.uniform(-8, 20, size=(m, 3))
+    pc_q = rng.uniform(-0.8, 0.8, size=m)
+    field = [0.05, -0.02, 0.1]
+    P = oracle.default_parameters()
+    chi, hard, rad, nq = oracle.gather(Z, P)
+    _, _, prad, pnq = oracle.gather(pcZ, P)
+    for basis in (1, 0):
+        ref = oracle.external_potential(xyz, rad, nq, pc_xyz, pc_q, prad, pnq, field, oracle.Options(basis=basis))
+        ext = _ffi.External()
+        ext.num_point_charges = m
+        pxyz = np.ascontiguousarray(pc_xyz); pq = np.ascontiguousarray(pc_q)
+        ext.xyz, ext.charge, ext.radius, ext.n = _ptr(pxyz), _ptr(pq), _ptr(prad), _ptr(pnq)
+        ext.field[0], ext.field[1], ext.field[2] = field
+        v = np.empty(len(Z))
+        x = np.ascontiguousarray(xyz)
+        rc = gpu_ctx._lib.cheq_external_potential(gpu_ctx.handle, len(Z), _ptr(x), _ptr(rad), _ptr(nq), C.byref(ext),
+                                                  0.5, basis, _ptr(v))
+        assert rc == 0, gpu_ctx.last_error()
+        assert np.max(np.abs(v - ref)) < 1e-11 * max(1.0, np.max(np.abs(ref)))
+
+
+# ---- full solves: Rappe-Goddard fixtures -----------------------------------------------------------------------
+@pytest.mark.parametrize("basis", [BasisType.Sto, BasisType.Gto])
+def test_rappe_goddard_parity_and_published_rows(gpu_ctx, oracle, rg_fixtures, basis):
+    key = "sto" if basis is BasisType.Sto else "gto"
+    s = solver(gpu_ctx, basis_type=basis)
+    checked = 0
+    worst = (0.0, 0.0)
+    for g in rg_fixtures["groups"]:
+        errs, perr = [], []
+        for c in g["cases"]:
+            res = s.solve(atoms_of(c["Z"], c["xyz"]), 0.0)
+            ref = oracle.solve(c["Z"], np.array(c["xyz"]), 0.0, oracle.Options(basis=basis.value))
+            dq, dmu = assert_parity(res, ref)
+            worst = (max(worst[0], dq), max(worst[1], dmu))
+            for p in c["published"]:
+                val = res.charges[p["index"]]
+                assert abs(round(val, 4) - p[key]) < 1e-9 or abs(val - p[key]) < 5.001e-5, (c["name"], p, val)
+                perr.append(abs(round(val, 4) - p["paper"]))
+                checked += 1
+            errs += [abs(res.charges[i] - q) for i, q in c["expected"]]
+        assert f"{np.mean(perr):.4f}" == f"{g['published_mae_' + key]:.4f}"
+        if basis is BasisType.Sto:       # tests/*.rs thresholds
+            assert np.mean(errs) <= g["avg_limit"] and np.max(errs) <= g["max_limit"]
+    assert checked == 67
+    print("worst |dq|, |dmu|:", worst)
+
+
+def test_indefinite_matrix_uses_pivoted_lu(gpu_ctx, oracle, rg_fixtures):
+    c = [c for g, c in rg_cases(rg_fixtures) if c["name"] == "C2H4"][0]
+    res = solver(gpu_ctx).solve(atoms_of(c["Z"], c["xyz"]), 0.0)
+    assert gpu_ctx.stats()["lu_fallback_frames"] == 1
+    assert_parity(res, oracle.solve(c["Z"], np.array(c["xyz"])))
+
+
+# ---- the reference's solver unit tests (implementation.rs:620-1013) -------------------------------------------
+def test_reference_solver_unit_tests(gpu_ctx):
+    s = solver(gpu_ctx)
+    r = s.solve([Atom(1, [0, 0, 0]), Atom(1, [0.74, 0, 0])], 0.0)
+    assert abs(r.charges[0]) < 1e-6 and abs(r.charges[0] - r.charges[1]) < 1e-10
+    hf = [Atom(1, [0, 0, 0]), Atom(9, [0.917, 0, 0])]
+    r = s.solve(hf, 0.0)
+    assert r.charges[0] > 0 > r.charges[1] and abs(sum(r.charges)) < 1e-6
+    water = [Atom(8, [0, 0, 0.1173]), Atom(1, [0, 0.7572, -0.4692]), Atom(1, [0, -0.7572, -0.4692])]
+    rs = s.solve(water, 0.0)
+    assert rs.charges[0] < -0.1 and rs.charges[1] > 0.05 and abs(rs.charges[1] - rs.charges[2]) < 1e-6
+    rg = solver(gpu_ctx, basis_type=BasisType.Gto).solve(water, 0.0)
+    assert abs(rs.charges[0] - rg.charges[0]) < 0.3
+    with pytest.raises(cheq_b200.NotConverged) as e:
+        solver(gpu_ctx, max_iterations=1).solve([Atom(3, [0, 0, 0]), Atom(1, [1.595, 0, 0])], 0.0)
+    assert e.value.max_iterations == 1 and e.value.delta > 1e-6
+    a = solver(gpu_ctx, damping=DampingStrategy.fixed(0.5)).solve(hf, 0.0)
+    b = solver(gpu_ctx, damping=DampingStrategy.none()).solve(hf, 0.0)
+    assert a.charges[0] > 0 and b.charges[0] > 0 and abs(a.charges[0] - b.charges[0]) < 0.01
+    g = solver(gpu_ctx, basis_type=BasisType.Gto).solve(hf, 0.0)
+    assert g.charges[0] > 0 > g.charges[1] and abs(sum(g.charges)) < 1e-6
+    # README example: neutrality to 1e-9 (lib.rs:57)
+    Z, xyz = workloads.readme_water()
+    r = s.solve(atoms_of(Z, xyz), 0.0)
+    assert r.charges[0] < 0 and abs(sum(r.charges)) < 1e-9
+
+
+def test_reference_solve_in_field_unit_tests(gpu_ctx):
+    s = solver(gpu_ctx)
+    hf = [Atom(1, [0, 0, 0]), Atom(9, [0.917, 0, 0])]
+    a = s.solve(hf, 0.0)
+    b = s.solve_in_field(hf, 0.0, ExternalPotential.new())
+    assert abs(a.charges[0] - b.charges[0]) < 1e-10 and abs(a.charges[1] - b.charges[1]) < 1e-10
+    co = [Atom(6, [0, 0, 0]), Atom(8, [1.2, 0, 0])]
+    vac = s.solve(co, 0.0)
+    f = s.solve_in_field(co, 0.0, ExternalPotential.from_point_charges([PointCharge.new(7, [3.0, 0, 0], 0.5)]))
+    assert f.charges[1] < vac.charges[1] and abs(sum(f.charges)) < 1e-6
+    hh = [Atom(1, [-0.37, 0, 0]), Atom(1, [0.37, 0, 0])]
+    sym = s.solve_in_field(hh, 0.0, ExternalPotential.from_point_charges(
+        [PointCharge.new(8, [0, 3.0, 0], 0.5), PointCharge.new(8, [0, -3.0, 0], 0.5)]))
+    assert abs(sym.charges[0] - sym.charges[1]) < 1e-6
+    e = s.solve_in_field(hf, 0.0, ExternalPotential.from_uniform_field([0.5, 0, 0]))
+    assert e.charges[0] < a.charges[0] and abs(sum(e.charges)) < 1e-6
+    both = ExternalPotential.new().with_point_charges([PointCharge.new(7, [3.0, 0, 0], 0.3)]).with_uniform_field([0.1, 0, 0])
+    assert abs(sum(s.solve_in_field(co, 0.0, both).charges)) < 1e-6
+    g = solver(gpu_ctx, basis_type=BasisType.Gto).solve_in_field(
+        co, 0.0, ExternalPotential.from_point_charges([PointCharge.new(7, [3.0, 0, 0], 0.5)]))
+    assert abs(sum(g.charges)) < 1e-6
+
+
+# ---- option coverage against the oracle -----------------------------------------------------------------------
+@pytest.mark.parametrize("opts", [
+    dict(), dict(basis_type=BasisType.Gto), dict(hydrogen_scf=False), dict(damping=DampingStrategy.none()),
+    dict(damping=DampingStrategy.fixed(0.5)), dict(damping=DampingStrategy.auto(0.9)), dict(lambda_scale=0.4913),
+    dict(tolerance=1e-10), dict(tolerance=1e-3),
+])
+def test_options_parity_on_clusters(gpu_ctx, oracle, opts):
+    o = SolverOptions(**opts)
+    s = QEqSolver(get_default_parameters(), o, gpu_ctx)
+    for (Z, xyz), Q in ((workloads.water_cluster(27), 0.0), (workloads.organic_chain(150), 1.0),
+                        (workloads.water_cluster(8), -2.0)):
+        res = s.solve(atoms_of(Z, xyz), Q)
+        ref = oracle.solve(Z, xyz, Q, oracle_opts(oracle, o))
+        assert_parity(res, ref)
+        assert abs(sum(res.charges) - Q) < 1e-8
+
+
+def test_water_375_and_heavy_elements(gpu_ctx, oracle):
+    Z, xyz = workloads.water_cluster(125)
+    res = solver(gpu_ctx).solve(atoms_of(Z, xyz), 0.0)
+    assert_parity(res, oracle.solve(Z, xyz))
+    rng = np.random.default_rng(5)
+    Zs = [11, 17] * 40 + [19, 35] * 20 + [26, 8, 8] * 10 + [1] * 30
+    pts = rng.uniform(0, 18, size=(4000, 3))
+    keep = [pts[0]]
+    for p in pts[1:]:
+        if len(keep) == len(Zs):
+            break
+        if min(np.linalg.norm(p - k) for k in keep) > 1.9:
+            keep.append(p)
+    xyz = np.array(keep)
+    assert len(xyz) == len(Zs)
+    res = solver(gpu_ctx).solve(atoms_of(Zs, xyz), 0.0)
+    assert_parity(res, oracle.solve(Zs, xyz))
+
+
+def test_b3k_field_and_point_charges(gpu_ctx, oracle):
+    """BASELINE config 3: 3,000-atom water cluster + uniform field + 10,000 embedding charges."""
+    Z, xyz, ext = workloads.water_box_3k()
+    ep = ExternalPotential.from_point_charges(
+        [PointCharge(int(z), p.tolist(), float(q)) for z, p, q in zip(ext["Z"], ext["xyz"], ext["q"])]
+    ).with_uniform_field(ext["field"])
+    res = solver(gpu_ctx).solve_in_field(atoms_of(Z, xyz), 0.0, ep)
+    ref = oracle.solve(Z, xyz, 0.0, external=ext)
+    assert_parity(res, ref)
+
+
+def test_batch_frames_parity(gpu_ctx, oracle):
+    Z, base = workloads.organic_chain(260)
+    frames = workloads.md_frames(base, 5)
+    s = solver(gpu_ctx)
+    q, mu, its, status = s.solve_batch(Z, frames, 0.0)
+    assert np.all(status == 0)
+    for f in range(len(frames)):
+        ref = oracle.solve(Z, frames[f])
+        assert its[f] == ref.iterations
+        assert np.max(np.abs(q[f] - ref.charges)) <= Q_TOL and abs(mu[f] - ref.equilibrated_potential) <= MU_TOL
+    single = s.solve(atoms_of(Z, frames[2]), 0.0)
+    assert np.max(np.abs(np.array(single.charges) - q[2])) < 1e-12
+
+
+# ---- full size: properties that need no oracle -----------------------------------------------------------------
+def test_s20k_properties(gpu_ctx, oracle):
+    """BASELINE headline size (20,001 atoms): neutrality, stationarity on sampled rows, permutation equivariance."""
+    Z, xyz = workloads.water_20k()
+    n = len(Z)
+    chi, hard, rad, nq = workloads.gather_parameters(Z, get_default_parameters())
+    s1 = QEqSolver(get_default_parameters(), SolverOptions(hydrogen_scf=False), gpu_ctx)
+    r = s1.solve_arrays(np.ascontiguousarray(xyz), chi, hard, rad, nq, 0.0)
+    q = np.array(r.charges)
+    assert r.iterations == 1 and abs(q.sum()) < 1e-8
+    # stationarity: chi_i + J_ii q_i + sum_j J_ij q_j + mu = 0 on 48 sampled rows, J from the CPU oracle
+    rng = np.random.default_rng(1)
+    for i in rng.choice(n, size=48, replace=False):
+        d = np.linalg.norm(xyz - xyz[i], axis=1) / BOHR
+        row = np.array([oracle.sto_integral(d[j], int(nq[i]), rad[i] / BOHR, int(nq[j]), rad[j] / BOHR, 0.5) * EV
+                        if j != i else hard[i] for j in range(n)])
+        assert abs(chi[i] + row @ q + r.equilibrated_potential) < 1e-8
+    # full SCF solve; permuting the atoms permutes the charges
+    s = solver(gpu_ctx)
+    full = s.solve_arrays(np.ascontiguousarray(xyz), chi, hard, rad, nq, 0.0)
+    assert 5 <= full.iterations <= 20 and abs(sum(full.charges)) < 1e-8
+    perm = rng.permutation(n)
+    pr = s.solve_arrays(np.ascontiguousarray(xyz[perm]), chi[perm], hard[perm], rad[perm], nq[perm], 0.0)
+    assert pr.iterations == full.iterations
+    assert np.max(np.abs(np.array(pr.charges) - np.array(full.charges)[perm])) < 1e-8
+    assert abs(pr.equilibrated_potential - full.equilibrated_potential) < 1e-8
