@@ -102,7 +102,7 @@ struct cheq_ctx {
     // device workspace (grow-only)
     DeviceBuffer in_xyz, in_chi, in_hard, in_radius, in_nq, perm, type, x, y, z, diag, chi, hard, vext, A, S0,
         Linv, v, q, scratch, counters, state, active, blob, pc_xyz, pc_q, pc_type, out_q, misc0, misc1, misc2,
-        lu_f, lu_piv;
+        lu_f, lu_piv, sgn;
     ScfState* h_state = nullptr;   // pinned
     int* h_active = nullptr;       // pinned
     size_t h_state_cap = 0;
@@ -334,8 +334,14 @@ struct Dense {
     int MT;
     ScfState* state;
     int batch;
+    double* sgn;        // [batch][NP] pivot signs of A = L S L^T
+    long strideSgn;
     double flops = 0.0;
 };
+
+// |pivot| below this (eV) is treated as a breakdown of the unpivoted factorisation -> pivoted-LU path.
+// Matrix entries are O(1..30) eV, so accepted pivots bound the element growth by ~1e5 (error ~1e-11).
+constexpr double kPivotTol = 1.0e-4;
 
 // Recursive tall-panel Cholesky of columns [j0, j0 + n) with all rows down to MT (the rows below the panel are
 // overwritten by A L^-T, i.e. the triangular solve is part of every leaf).
@@ -345,7 +351,8 @@ int factor_panel(Dense& D, int j0, int n) {
     if (n == kTile) {
         double* Ajj = D.A + (long)j0 + (long)j0 * D.ld;
         double* Lk = D.Linv + (long)(j0 / kTile) * kTile * kTile;
-        LAUNCH(launch_potrf_tile(Ajj, D.ld, D.strideA, Lk, D.strideLinv, D.state, D.batch, ctx->stream));
+        LAUNCH(launch_potrf_tile(Ajj, D.ld, D.strideA, Lk, D.strideLinv, D.sgn + j0, D.strideSgn, D.state, kPivotTol,
+                                 D.batch, ctx->stream));
         const int mt = (D.MT - j0 - kTile) / kTile;
         if (mt > 0) {
             GemmArgs g{};
@@ -386,6 +393,8 @@ int factor_panel(Dense& D, int j0, int n) {
         g.K = n1;
         g.lower = 1;
         g.subtract = 1;
+        g.sgn = D.sgn + j0;
+        g.strideSgn = D.strideSgn;
         g.state = D.state;
         const int mt = (D.MT - r0) / kTile, nt = (n - n1) / kTile;
         LAUNCH(launch_gemm_nt(g, mt, nt, D.batch, ctx->stream));
@@ -412,6 +421,8 @@ int schur_update(Dense& D, int k, int ncols) {
     g.K = k;
     g.lower = 1;
     g.subtract = 1;
+    g.sgn = D.sgn;
+    g.strideSgn = D.strideSgn;
     g.state = D.state;
     LAUNCH(launch_gemm_nt(g, (D.MT - k) / kTile, ncols / kTile, D.batch, ctx->stream));
     const double w = (double)ncols, m = (double)(D.MT - k);
@@ -422,7 +433,7 @@ int schur_update(Dense& D, int k, int ncols) {
 int backsolve(Dense& D, int NP, double* v, long v_stride) {
     cheq_ctx* ctx = D.ctx;
     for (int kb = NP / kTile - 1; kb >= 0; --kb)
-        LAUNCH(launch_backsolve_step(D.A, D.ld, D.strideA, D.Linv, D.strideLinv, NP, kb, v, v_stride,
+        LAUNCH(launch_backsolve_step(D.A, D.ld, D.strideA, D.Linv, D.strideLinv, D.sgn, D.strideSgn, NP, kb, v, v_stride,
                                      ctx->scratch.as<double>(), (long)backsolve_max_ctas() * kTile,
                                      ctx->counters.as<unsigned>(), D.state, D.batch, ctx->stream));
     return CHEQ_OK;
@@ -562,6 +573,7 @@ int prepare_and_assemble(cheq_ctx* ctx, const SolveIO& io, long frame0, int batc
     CU(ctx->hard.ensure(L.NP * 8));
     CU(ctx->scratch.ensure((size_t)backsolve_max_ctas() * kTile * 8 * batch));
     CU(ctx->counters.ensure(sizeof(unsigned) * batch));
+    CU(ctx->sgn.ensure(vec));
     CU(ctx->state.ensure(sizeof(ScfState) * batch));
     CU(ctx->active.ensure(sizeof(int)));
     int rc = ensure_host_state(ctx, batch);
@@ -667,7 +679,7 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
     cudaStream_t st = ctx->stream;
     const int batch = P.batch;
     Dense D{ctx, ctx->A.as<double>(), L.ld, P.strideA, ctx->Linv.as<double>(), (long)L.NP * kTile, L.MT,
-            ctx->state.as<ScfState>(), batch};
+            ctx->state.as<ScfState>(), batch, ctx->sgn.as<double>(), (long)L.NP};
     double damping0 = 1.0;   // implementation.rs:297-301
     if (L.scf && o.damping_kind != CHEQ_DAMPING_NONE) damping0 = o.damping_value;
     LAUNCH(launch_scf_init(ctx->state.as<ScfState>(), damping0, batch, st));
@@ -680,7 +692,7 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
         rc = factor_panel(D, 0, L.NP);
         if (rc) return rc;
         CU(cudaEventRecord(ctx->ev[3], st));
-        LAUNCH(launch_mu(D.A, D.ld, D.strideA, L.NP, io.total_charge, v, L.NP, D.state, batch, st));
+        LAUNCH(launch_mu(D.A, D.ld, D.strideA, L.NP, io.total_charge, v, L.NP, D.sgn, D.strideSgn, D.state, batch, st));
         rc = backsolve(D, L.NP, v, L.NP);
         if (rc) return rc;
         LAUNCH(launch_scf_mix(v, q, L.NP, ctx->type.as<uint8_t>(), L.NP, D.state, batch, st));
@@ -722,7 +734,7 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
         D.flops = 0.0;
         rc = factor_panel(D, L.nxp, L.nhp);
         if (rc) return rc;
-        LAUNCH(launch_mu(D.A, D.ld, D.strideA, L.NP, io.total_charge, v, L.NP, D.state, batch, st));
+        LAUNCH(launch_mu(D.A, D.ld, D.strideA, L.NP, io.total_charge, v, L.NP, D.sgn, D.strideSgn, D.state, batch, st));
         rc = backsolve(D, L.NP, v, L.NP);
         if (rc) return rc;
         LAUNCH(launch_scf_mix(v, q, L.NP, ctx->type.as<uint8_t>(), L.NP, D.state, batch, st));
@@ -949,7 +961,7 @@ void cheq_ctx_destroy(cheq_ctx* ctx) {
                             &ctx->type, &ctx->x, &ctx->y, &ctx->z, &ctx->diag, &ctx->chi, &ctx->hard, &ctx->vext,
                             &ctx->A, &ctx->S0, &ctx->Linv, &ctx->v, &ctx->q, &ctx->scratch, &ctx->counters,
                             &ctx->state, &ctx->active, &ctx->blob, &ctx->pc_xyz, &ctx->pc_q, &ctx->pc_type,
-                            &ctx->out_q, &ctx->misc0, &ctx->misc1, &ctx->misc2, &ctx->lu_f, &ctx->lu_piv};
+                            &ctx->out_q, &ctx->misc0, &ctx->misc1, &ctx->misc2, &ctx->lu_f, &ctx->lu_piv, &ctx->sgn};
     for (DeviceBuffer* b : bufs) b->release();
     if (ctx->h_state) cudaFreeHost(ctx->h_state);
     if (ctx->h_active) cudaFreeHost(ctx->h_active);
@@ -1237,8 +1249,9 @@ int32_t cheq_dbg_cholesky_solve(cheq_ctx* ctx, uint64_t n_, const double* a, uin
     CU(cudaMemsetAsync(ctx->counters.p, 0, sizeof(unsigned), st));
     CU(cudaMemcpyAsync(ctx->A.p, h.data(), h.size() * 8, cudaMemcpyHostToDevice, st));
     LAUNCH(launch_scf_init(ctx->state.as<ScfState>(), 1.0, 1, st));
+    CU(ctx->sgn.ensure(NP * 8));
     Dense D{ctx, ctx->A.as<double>(), ld, (long)ld * NP, ctx->Linv.as<double>(), (long)NP * kTile, MT,
-            ctx->state.as<ScfState>(), 1};
+            ctx->state.as<ScfState>(), 1, ctx->sgn.as<double>(), (long)NP};
     rc = factor_panel(D, 0, NP);
     if (rc) return rc;
     std::vector<double> xv(NP);

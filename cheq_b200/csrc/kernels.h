@@ -47,7 +47,9 @@ struct GemmArgs {
     long strideA, strideB, strideC;  // per frame
     int K;
     int lower;                 // 1: skip tiles strictly above the diagonal of C
-    int subtract;              // 1: C -= A B^T ; 0: C = A B^T (C may alias A when the grid has one tile column)
+    int subtract;              // 1: C -= A S B^T ; 0: C = A S B^T (C may alias A when the grid has one tile column)
+    const double* sgn;         // nullable: S = diag(+-1) over the K range (pivot signs of A = L S L^T)
+    long strideSgn;
     const ScfState* state;     // nullable; frames with active == 0 are skipped
 };
 
@@ -68,9 +70,10 @@ cudaError_t launch_export_matrix(int NP, long ld, const double* A, const int* pe
 
 // ---- dense (kernels_dense.cu) ------------------------------------------------------------------------------
 cudaError_t launch_gemm_nt(const GemmArgs& g, int m_tiles, int n_tiles, int batch, cudaStream_t stream);
-// Cholesky of one 128 x 128 diagonal block in place (lower) + its inverse (dense 128 x 128, ld 128).
-cudaError_t launch_potrf_tile(double* A, long lda, long strideA, double* Linv, long strideLinv, ScfState* state,
-                              int batch, cudaStream_t stream);
+// A = L S L^T of one 128 x 128 diagonal block in place (lower) + M = S L^-1 (dense 128 x 128, ld 128) + the signs.
+// |pivot| <= pivot_tol sets state.info (the caller then falls back to the pivoted LU).
+cudaError_t launch_potrf_tile(double* A, long lda, long strideA, double* Linv, long strideLinv, double* sgn,
+                              long strideSgn, ScfState* state, double pivot_tol, int batch, cudaStream_t stream);
 // copies the tiles on/below the diagonal of an (m_tiles x n_tiles) tile region
 cudaError_t launch_copy_lower_tiles(const double* src, long lds, long stride_src, double* dst, long ldd,
                                     long stride_dst, int m_tiles, int n_tiles, const ScfState* state, int batch,
@@ -81,11 +84,13 @@ cudaError_t launch_set_h_diagonal(double* A, long lda, long strideA, const doubl
                                   int nhp, const ScfState* state, int batch, cudaStream_t stream);
 // mu = (f1.fc - Q) / (f1.f1) from rows NP, NP+1; v = fc - mu f1
 cudaError_t launch_mu(const double* A, long lda, long strideA, int NP, double total_charge, double* v,
-                      long v_stride, ScfState* state, int batch, cudaStream_t stream);
+                      long v_stride, const double* sgn, long strideSgn, ScfState* state, int batch,
+                      cudaStream_t stream);
 // one block-row step (block kb) of the backward substitution L^T x = v, in place in v
 cudaError_t launch_backsolve_step(const double* A, long lda, long strideA, const double* Linv, long strideLinv,
-                                  int NP, int kb, double* v, long v_stride, double* scratch, long scratch_stride,
-                                  unsigned* counters, const ScfState* state, int batch, cudaStream_t stream);
+                                  const double* sgn, long strideSgn, int NP, int kb, double* v, long v_stride,
+                                  double* scratch, long scratch_stride, unsigned* counters, const ScfState* state,
+                                  int batch, cudaStream_t stream);
 int backsolve_max_ctas();
 // delta = max |x - q| over real atoms; q <- (1 - d) q + d x
 cudaError_t launch_scf_mix(const double* x, double* q, long stride, const uint8_t* type, int NP, ScfState* state,

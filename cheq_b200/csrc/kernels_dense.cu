@@ -48,6 +48,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_nt_kernel(GemmArgs g) {
     extern __shared__ __align__(16) double smem[];
     double* As = smem;                          // [STAGES][BK][LDT]
     double* Bs = smem + STAGES * BK * LDT;      // [STAGES][BK][LDT]
+    __shared__ double sgs[STAGES][BK];          // pivot signs of the K range (A = L S L^T), 1 if absent
+    const double* sgn = g.sgn ? g.sgn + (long)frame * g.strideSgn : nullptr;
 
     const double* A = g.A + (long)frame * g.strideA + (long)tile_m * BM;
     const double* B = g.B + (long)frame * g.strideB + (long)tile_n * BN;
@@ -68,6 +70,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_nt_kernel(GemmArgs g) {
             cp_async16(as + kr * LDT + 2 * mc, A + 2 * mc + (k0 + kr) * g.lda);
             cp_async16(bs + kr * LDT + 2 * mc, B + 2 * mc + (k0 + kr) * g.ldb);
         }
+        if (t < BK) sgs[stage][t] = sgn ? sgn[k0 + t] : 1.0;
     };
 
     double acc[4][2][2][2][2];  // [fm][row parity][fn][col parity][e]
@@ -98,6 +101,12 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_nt_kernel(GemmArgs g) {
             for (int fm = 0; fm < 4; ++fm) a[fm] = *(const double2*)(as + (kk * 4 + q) * LDT + fm * 16);
 #pragma unroll
             for (int fn = 0; fn < 2; ++fn) b[fn] = *(const double2*)(bs + (kk * 4 + q) * LDT + fn * 16);
+            const double sv = sgs[it % STAGES][kk * 4 + q];
+#pragma unroll
+            for (int fn = 0; fn < 2; ++fn) {
+                b[fn].x *= sv;
+                b[fn].y *= sv;
+            }
 #pragma unroll
             for (int fm = 0; fm < 4; ++fm)
 #pragma unroll
@@ -136,69 +145,120 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_nt_kernel(GemmArgs g) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// 128 x 128 diagonal block: Cholesky (lower, in place) and the inverse of the factor, one CTA.
-// Shared array S[col * 128 + row]: the lower triangle holds A -> L, the strict upper triangle holds the strict
-// lower triangle of X = L^-1 transposed in place (X_ij, i > j, at S[i * 128 + j]); diag(X) in dinv.
-// Step k finalises column k of L, then applies the rank-1 updates of both the trailing matrix and of X.
+// 128 x 128 diagonal block, one CTA: A = L S L^T (S = diag(+-1): Cholesky that tolerates negative pivots, i.e.
+// LDL^T without pivoting; the hardness + Coulomb matrix of a large cluster is symmetric but not always positive
+// definite) together with M = S L^-1, which turns the triangular solves of the rows below into a GEMM.
+//
+// The whole tile lives in registers: thread (ty, tx) of a 16 x 16 grid owns the 64 elements
+// (r, c) = (ty + 16 a, tx + 16 b).  For r >= c the element is A -> L; the strict upper part (r < c) holds
+// X[c][r], X = L^-1 (forward elimination on the identity).  Step k scales logical column k by s/l -- it is owned by
+// one half-warp, which gets the pivot by shuffle -- and publishes it as u[0..127]; then every element with c > k
+// and (r >= c or r <= k) takes  e -= s u[r] u[c].  One __syncthreads per step (u is double buffered).
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kPotrfThreads = 256;
-constexpr int kPotrfSmem = (kTile * kTile + kTile) * (int)sizeof(double);
+constexpr int kPotrfLd = kTile + 1;
+constexpr int kPotrfSmem = kTile * kPotrfLd * (int)sizeof(double);
 
 __global__ void __launch_bounds__(kPotrfThreads)
-potrf_tile_kernel(double* A_, long lda, long strideA, double* Linv_, long strideLinv, ScfState* state) {
+potrf_tile_kernel(double* A_, long lda, long strideA, double* Minv_, long strideM, double* sgn_, long strideSgn,
+                  ScfState* state, double pivot_tol) {
     const int frame = blockIdx.z;
     if (state && !state[frame].active) return;
-    extern __shared__ __align__(16) double S[];
-    double* dinv = S + kTile * kTile;
+    extern __shared__ __align__(16) double Ms[];   // staging of M for a coalesced store
+    __shared__ double ubuf[2][kTile];
+    __shared__ double dinv[kTile];
+    __shared__ double sg[kTile];
     double* A = A_ + (long)frame * strideA;
-    double* Linv = Linv_ + (long)frame * strideLinv;
-    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    double* Minv = Minv_ + (long)frame * strideM;
+    const int t = threadIdx.x;
+    const int ty = t & 15, tx = t >> 4;
 
-    for (int idx = t; idx < kTile * kTile; idx += kPotrfThreads) {
-        const int i = idx & (kTile - 1), j = idx >> 7;
-        S[idx] = (i >= j) ? A[i + (long)j * lda] : 0.0;
+    double e[8][8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b)
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const int r = ty + 16 * a, c = tx + 16 * b;
+            e[a][b] = (r >= c) ? A[r + (long)c * lda] : 0.0;
+        }
+
+    int cur = 0;
+#pragma unroll
+    for (int kb = 0; kb < 8; ++kb) {
+        for (int kt = 0; kt < 16; ++kt) {
+            const int k = kb * 16 + kt;
+            // pivot: element (k, k) lives in thread (ty = kt, tx = kt), register e[kb][kb]
+            const double d = __shfl_sync(0xffffffffu, e[kb][kb], kt + 16 * (tx & 1));
+            if (tx == kt) {
+                const double ad = fabs(d);
+                const bool bad = !(ad > pivot_tol) || !(ad < 1.0e300);
+                const double sgnk = (d < 0.0) ? -1.0 : 1.0;
+                const double l = bad ? 1.0 : sqrt(ad);
+                const double il = 1.0 / l;
+                const double sil = sgnk * il;
+                if (ty == kt) {
+                    dinv[k] = il;
+                    sg[k] = sgnk;
+                    if (bad && state) atomicExch(&state[frame].info, k + 1);
+                }
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    const int r = ty + 16 * a;
+                    const double v = e[a][kb];
+                    double u;
+                    if (r == k) {
+                        u = sil;
+                        e[a][kb] = l;
+                    } else {
+                        u = v * sil;
+                        e[a][kb] = (r > k) ? u : v * il;   // L column below the pivot / row k of X
+                    }
+                    ubuf[cur][r] = u;
+                }
+            }
+            __syncthreads();
+            const double sk = sg[k];
+            double su[8];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) su[a] = sk * ubuf[cur][ty + 16 * a];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                if (b < kb) continue;
+                const int c = tx + 16 * b;
+                if (c > k) {
+                    const double uc = ubuf[cur][c];
+#pragma unroll
+                    for (int a = 0; a < 8; ++a) {
+                        const int r = ty + 16 * a;
+                        if (r >= c || r <= k) e[a][b] = fma(-su[a], uc, e[a][b]);
+                    }
+                }
+            }
+            cur ^= 1;
+        }
     }
     __syncthreads();
 
-    for (int k = 0; k < kTile; ++k) {
-        const double d = S[k * kTile + k];
-        const bool bad = !(d > 0.0) || !(d < 1.7e308);
-        if (bad && t == 0 && state) atomicExch(&state[frame].info, k + 1);
-        const double l = bad ? 1.0 : sqrt(d);
-        const double inv = 1.0 / l;
-        __syncthreads();  // everybody has read d
-        if (t >= k && t < kTile) S[k * kTile + t] = (t == k) ? l : S[k * kTile + t] * inv;   // column k of L
-        if (t > kTile && t - kTile <= k) {                                                  // row k of X
-            const int j = t - kTile - 1;   // 0..k-1
-            if (j < k) S[k * kTile + j] *= inv;
+    // L back to global; M = S X staged through shared memory (M[i][j] = s_i X[i][j], i > j, held as element (j, i))
+#pragma unroll
+    for (int b = 0; b < 8; ++b)
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const int r = ty + 16 * a, c = tx + 16 * b;
+            if (r >= c) A[r + (long)c * lda] = e[a][b];
+            // Ms[j * ld + i] = M[i][j]; the holder of (r, c) fills M[c][r]: X part below the diagonal of M,
+            // the diagonal, and zeros above it
+            double m = 0.0;
+            if (r < c) m = sg[c] * e[a][b];
+            else if (r == c) m = sg[r] * dinv[r];
+            Ms[r * kPotrfLd + c] = m;
         }
-        if (t == kTile) dinv[k] = inv;
-        __syncthreads();
-        // trailing update of A: S[j][i] -= L_ik L_jk, k < j <= i
-        for (int j = k + 1 + warp; j < kTile; j += kPotrfThreads / 32) {
-            const double ljk = S[k * kTile + j];
-            for (int i = j + lane; i < kTile; i += 32) S[j * kTile + i] -= S[k * kTile + i] * ljk;
-        }
-        // update of X: X_ij -= L_ik X_kj for i > k, j <= k   (X_kk = dinv[k], X_ik starts at 0)
-        const int w = k + 1;   // row k of X has k + 1 entries
-        for (int e = t; e < (kTile - 1 - k) * w; e += kPotrfThreads) {
-            const int i = k + 1 + e / w, j = e - (e / w) * w;
-            const double xkj = (j == k) ? inv : S[k * kTile + j];
-            S[i * kTile + j] -= S[k * kTile + i] * xkj;
-        }
-        // no barrier needed here: the next iteration's first barrier orders these writes before its reads of
-        // column k+1 / row k+1?  Not so -- d is read before that barrier, hence:
-        __syncthreads();
-    }
-
+    __syncthreads();
     for (int idx = t; idx < kTile * kTile; idx += kPotrfThreads) {
         const int i = idx & (kTile - 1), j = idx >> 7;
-        if (i >= j) A[i + (long)j * lda] = S[idx];
-        double x = 0.0;
-        if (i > j) x = S[i * kTile + j];
-        else if (i == j) x = dinv[i];
-        Linv[idx] = x;
+        Minv[idx] = Ms[j * kPotrfLd + i];
     }
+    if (t < kTile && sgn_) sgn_[(long)frame * strideSgn + t] = sg[t];
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -234,19 +294,21 @@ __global__ void set_h_diagonal_kernel(double* A, long lda, long strideA, const d
 // mu and the combined right-hand side.  One CTA per frame; fixed summation order.
 __global__ void __launch_bounds__(1024)
 mu_kernel(const double* A_, long lda, long strideA, int NP, double total_charge, double* v_, long v_stride,
-          ScfState* state) {
+          const double* sgn_, long strideSgn, ScfState* state) {
     const int frame = blockIdx.z;
     if (!state[frame].active) return;
     const double* fc = A_ + (long)frame * strideA + NP;   // row NP
     const double* f1 = fc + 1;                            // row NP + 1
     double* v = v_ + (long)frame * v_stride;
+    const double* sgn = sgn_ + (long)frame * strideSgn;
     __shared__ double s11[32], s1c[32];
     __shared__ double mu_s;
     double a11 = 0.0, a1c = 0.0;
     for (int j = threadIdx.x; j < NP; j += 1024) {
-        const double x1 = f1[(long)j * lda], xc = fc[(long)j * lda];
-        a11 = fma(x1, x1, a11);
-        a1c = fma(x1, xc, a1c);
+        // rows hold y = S L^-1 b, so b^T A^-1 c = sum_k s_k y_b[k] y_c[k]
+        const double x1 = f1[(long)j * lda], xc = fc[(long)j * lda], sx1 = sgn[j] * x1;
+        a11 = fma(sx1, x1, a11);
+        a1c = fma(sx1, xc, a1c);
     }
     for (int off = 16; off > 0; off >>= 1) {
         a11 += __shfl_xor_sync(0xffffffffu, a11, off);
@@ -272,16 +334,21 @@ mu_kernel(const double* A_, long lda, long strideA, int NP, double total_charge,
     for (int j = threadIdx.x; j < NP; j += 1024) v[j] = fc[(long)j * lda] - mu * f1[(long)j * lda];
 }
 
-// Backward substitution, block row kb:  x_kb = Linv_kb^T (v_kb - L[rows below, kb cols]^T x[rows below]).
-constexpr int kBackMaxCtas = 32;
+// Backward substitution L^T x = v, block row kb:  x_kb = L_kk^-T (v_kb - L[rows below, kb cols]^T x[rows below]),
+// with L_kk^-T t = M_kk^T (S t).  Each CTA reduces a 256-row slab of the panel (every warp keeps 4 columns x 2 row
+// groups in flight), writes its 128 partial sums, and the last CTA to finish adds them in fixed order and applies
+// the diagonal block.
+constexpr int kBackMaxCtas = 160;
+constexpr int kBackRows = 256;
 __global__ void __launch_bounds__(256)
-backsolve_step_kernel(const double* A_, long lda, long strideA, const double* Linv_, long strideLinv, int NP,
-                      int kb, double* v_, long v_stride, double* scratch_, long scratch_stride,
-                      unsigned* counters, const ScfState* state) {
+backsolve_step_kernel(const double* A_, long lda, long strideA, const double* Minv_, long strideM,
+                      const double* sgn_, long strideSgn, int NP, int kb, double* v_, long v_stride,
+                      double* scratch_, long scratch_stride, unsigned* counters, const ScfState* state) {
     const int frame = blockIdx.z;
     if (state && !state[frame].active) return;
     const double* A = A_ + (long)frame * strideA;
-    const double* Linv = Linv_ + (long)frame * strideLinv + (long)kb * kTile * kTile;
+    const double* Minv = Minv_ + (long)frame * strideM + (long)kb * kTile * kTile;
+    const double* sgn = sgn_ + (long)frame * strideSgn + kb * kTile;
     double* v = v_ + (long)frame * v_stride;
     double* scratch = scratch_ + (long)frame * scratch_stride;
     const int G = gridDim.x, c = blockIdx.x;
@@ -289,16 +356,40 @@ backsolve_step_kernel(const double* A_, long lda, long strideA, const double* Li
     const int r_lo = (kb + 1) * kTile;
     const int rows = NP - r_lo;
     int chunk = (rows + G - 1) / G;
-    chunk = (chunk + 31) & ~31;
+    chunk = (chunk + 63) & ~63;
     const int r0 = r_lo + c * chunk;
     const int r1 = min(NP, r0 + chunk);
+    __shared__ double xs[kBackRows * 4];   // slab of x (chunk <= 1024 rows by construction of G)
+    for (int r = r0 + t; r < r1; r += 256) xs[r - r0] = v[r];
+    __syncthreads();
 
-    for (int col = warp; col < kTile; col += 8) {
-        const double* Lc = A + (long)(kb * kTile + col) * lda;
-        double s = 0.0;
-        for (int r = r0 + lane; r < r1; r += 32) s = fma(Lc[r], v[r], s);
-        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-        if (lane == 0) scratch[c * kTile + col] = s;
+    for (int cg = 0; cg < 4; ++cg) {
+        const int col = warp * 16 + cg * 4;
+        const double* L0 = A + (long)(kb * kTile + col) * lda;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int r = r0 + lane;
+        for (; r + 32 < r1; r += 64) {
+            const double xa = xs[r - r0], xb = xs[r + 32 - r0];
+            const double a0 = L0[r], a1 = L0[r + lda], a2 = L0[r + 2 * lda], a3 = L0[r + 3 * lda];
+            const double b0 = L0[r + 32], b1 = L0[r + 32 + lda], b2 = L0[r + 32 + 2 * lda], b3 = L0[r + 32 + 3 * lda];
+            s0 = fma(a0, xa, s0); s1 = fma(a1, xa, s1); s2 = fma(a2, xa, s2); s3 = fma(a3, xa, s3);
+            s0 = fma(b0, xb, s0); s1 = fma(b1, xb, s1); s2 = fma(b2, xb, s2); s3 = fma(b3, xb, s3);
+        }
+        for (; r < r1; r += 32) {
+            const double xa = xs[r - r0];
+            s0 = fma(L0[r], xa, s0); s1 = fma(L0[r + lda], xa, s1);
+            s2 = fma(L0[r + 2 * lda], xa, s2); s3 = fma(L0[r + 3 * lda], xa, s3);
+        }
+        for (int off = 16; off > 0; off >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+            s3 += __shfl_xor_sync(0xffffffffu, s3, off);
+        }
+        if (lane == 0) {
+            double* o = scratch + c * kTile + col;
+            o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3;
+        }
     }
     __shared__ bool is_last;
     __shared__ double tv[kTile];
@@ -314,12 +405,12 @@ backsolve_step_kernel(const double* A_, long lda, long strideA, const double* Li
     if (t < kTile) {
         double s = 0.0;
         for (int cc = 0; cc < G; ++cc) s += __ldcg(&scratch[cc * kTile + t]);
-        tv[t] = v[kb * kTile + t] - s;
+        tv[t] = sgn[t] * (v[kb * kTile + t] - s);
     }
     __syncthreads();
     for (int i = warp; i < kTile; i += 8) {
-        // x_i = sum_{j >= i} Linv[j, i] tv[j]
-        const double* Xc = Linv + (long)i * kTile;
+        // x_i = sum_{j >= i} M[j, i] (S t)[j]
+        const double* Xc = Minv + (long)i * kTile;
         double s = 0.0;
         for (int j = i + lane; j < kTile; j += 32) s = fma(Xc[j], tv[j], s);
         for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
@@ -413,8 +504,8 @@ cudaError_t launch_gemm_nt(const GemmArgs& g, int m_tiles, int n_tiles, int batc
     return cudaGetLastError();
 }
 
-cudaError_t launch_potrf_tile(double* A, long lda, long strideA, double* Linv, long strideLinv, ScfState* state,
-                              int batch, cudaStream_t stream) {
+cudaError_t launch_potrf_tile(double* A, long lda, long strideA, double* Linv, long strideLinv, double* sgn,
+                              long strideSgn, ScfState* state, double pivot_tol, int batch, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e =
@@ -423,7 +514,8 @@ cudaError_t launch_potrf_tile(double* A, long lda, long strideA, double* Linv, l
         configured = true;
     }
     dim3 grid(1, 1, batch);
-    potrf_tile_kernel<<<grid, kPotrfThreads, kPotrfSmem, stream>>>(A, lda, strideA, Linv, strideLinv, state);
+    potrf_tile_kernel<<<grid, kPotrfThreads, kPotrfSmem, stream>>>(A, lda, strideA, Linv, strideLinv, sgn, strideSgn,
+                                                                   state, pivot_tol);
     return cudaGetLastError();
 }
 
@@ -447,24 +539,28 @@ cudaError_t launch_set_h_diagonal(double* A, long lda, long strideA, const doubl
 }
 
 cudaError_t launch_mu(const double* A, long lda, long strideA, int NP, double total_charge, double* v,
-                      long v_stride, ScfState* state, int batch, cudaStream_t stream) {
+                      long v_stride, const double* sgn, long strideSgn, ScfState* state, int batch,
+                      cudaStream_t stream) {
     dim3 grid(1, 1, batch);
-    mu_kernel<<<grid, 1024, 0, stream>>>(A, lda, strideA, NP, total_charge, v, v_stride, state);
+    mu_kernel<<<grid, 1024, 0, stream>>>(A, lda, strideA, NP, total_charge, v, v_stride, sgn, strideSgn, state);
     return cudaGetLastError();
 }
 
 int backsolve_max_ctas() { return kBackMaxCtas; }
 
 cudaError_t launch_backsolve_step(const double* A, long lda, long strideA, const double* Linv, long strideLinv,
-                                  int NP, int kb, double* v, long v_stride, double* scratch, long scratch_stride,
-                                  unsigned* counters, const ScfState* state, int batch, cudaStream_t stream) {
+                                  const double* sgn, long strideSgn, int NP, int kb, double* v, long v_stride,
+                                  double* scratch, long scratch_stride, unsigned* counters, const ScfState* state,
+                                  int batch, cudaStream_t stream) {
     const int rows = NP - (kb + 1) * kTile;
-    int G = (rows + 511) / 512;
+    int G = (rows + kBackRows - 1) / kBackRows;
     if (G < 1) G = 1;
     if (G > kBackMaxCtas) G = kBackMaxCtas;
+    // the x slab staged in shared memory holds at most 4 * kBackRows rows per CTA
+    while ((((rows + G - 1) / G + 63) & ~63) > 4 * kBackRows) ++G;
     dim3 grid(G, 1, batch);
-    backsolve_step_kernel<<<grid, 256, 0, stream>>>(A, lda, strideA, Linv, strideLinv, NP, kb, v, v_stride,
-                                                    scratch, scratch_stride, counters, state);
+    backsolve_step_kernel<<<grid, 256, 0, stream>>>(A, lda, strideA, Linv, strideLinv, sgn, strideSgn, NP, kb, v,
+                                                    v_stride, scratch, scratch_stride, counters, state);
     return cudaGetLastError();
 }
 

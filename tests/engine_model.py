@@ -36,19 +36,25 @@ def solve_model(A, chi_plus_v, hard, nq, total_charge, tolerance=1e-6, max_itera
     one[idx] = 1.0
     T = np.vstack([M, c, one])  # trapezoid (NP + 2) x NP
 
+    sgn = np.ones(NP)
+
     def factor(T, j0, j1):
-        """in-place Cholesky of columns [j0, j1) of the trapezoid, rows below included"""
+        """in-place A = L S L^T (S = +-1, no pivoting) of columns [j0, j1) of the trapezoid, rows below included"""
         for j in range(j0, j1):
             d = T[j, j]
-            if not d > 0:
-                raise np.linalg.LinAlgError("not SPD")
-            T[j:, j] /= np.sqrt(d)
-            T[j + 1:, j + 1:j1] -= np.outer(T[j + 1:, j], T[j + 1:j1, j])
+            if not abs(d) > 1e-4:
+                raise np.linalg.LinAlgError("vanishing pivot")
+            s = -1.0 if d < 0 else 1.0
+            sgn[j] = s
+            l = np.sqrt(abs(d))
+            T[j + 1:, j] *= s / l
+            T[j, j] = l
+            T[j + 1:, j + 1:j1] -= s * np.outer(T[j + 1:, j], T[j + 1:j1, j])
         return T
 
     def finish(T):
-        fc, f1 = T[NP, :], T[NP + 1, :]
-        mu = (f1 @ fc - total_charge) / (f1 @ f1)
+        fc, f1 = T[NP, :], T[NP + 1, :]           # y = S L^-1 b
+        mu = ((sgn * f1) @ fc - total_charge) / ((sgn * f1) @ f1)
         v = fc - mu * f1
         L = np.tril(T[:NP, :])
         x = np.linalg.solve(L.T, v)
@@ -62,7 +68,7 @@ def solve_model(A, chi_plus_v, hard, nq, total_charge, tolerance=1e-6, max_itera
         out[perm[idx]] = x[idx]
         return out, mu, 1
     T = factor(T, 0, nxp)
-    T[nxp:, nxp:] -= T[nxp:, :nxp] @ T[nxp:NP, :nxp].T
+    T[nxp:, nxp:] -= (T[nxp:, :nxp] * sgn[:nxp]) @ T[nxp:NP, :nxp].T
     S0 = T[nxp:, nxp:].copy()
     hard_p = np.zeros(NP)
     hard_p[idx] = hard[perm[idx]]

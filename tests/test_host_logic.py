@@ -163,8 +163,6 @@ def test_engine_algebra_model_matches_oracle(oracle, rg_fixtures):
     from engine_model import solve_model
     P = oracle.default_parameters()
     for g, c in rg_cases(rg_fixtures):
-        if c["name"] == "C2H4":
-            continue   # indefinite matrix (coincident hydrogens in the reference fixture): pivoted-LU path
         xyz = np.array(c["xyz"])
         chi, hard, rad, nq = oracle.gather(c["Z"], P)
         ref = oracle.solve(c["Z"], xyz)
@@ -176,7 +174,7 @@ def test_engine_algebra_model_matches_oracle(oracle, rg_fixtures):
 
 
 def test_c2h4_fixture_is_indefinite(oracle, rg_fixtures):
-    """Documents why the engine carries a pivoted-LU path: the reference's own C2H4 geometry is not SPD."""
+    """Documents why the factorisation carries pivot signs: the reference's own C2H4 geometry is not SPD."""
     P = oracle.default_parameters()
     c = [c for g, c in rg_cases(rg_fixtures) if c["name"] == "C2H4"][0]
     chi, hard, rad, nq = oracle.gather(c["Z"], P)
