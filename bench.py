@@ -1,0 +1,385 @@
+#!/usr/bin/env python3
+"""Headline benchmark: QEq solve time at N = 20,001 atoms, STO shielding, fp64 (BASELINE.json `metric`).
+
+A step = one full `QEqSolver::solve` of the S20k workload (6,667-water open cluster):
+assembly of the shielded-Coulomb matrix, factorisation, the complete hydrogen SCF loop, charges out.
+
+  value      seconds per solve with the per-atom inputs already resident in HBM (cheq_solve_device)
+  e2e        the same through the public API with host (pinned) buffers: H2D of the inputs and D2H of the charges
+             inside the timed region (cheq_solve)
+  roofline   the dominant kernel (gemm_nt_kernel, FP64 DMMA): algorithmic flops / summed launch durations, both
+             measured live with CUDA events on the engine's stream; peak = cuBLAS DGEMM measured in the same run
+             (MEASURED_PEAKS.json has no fp64 entry)
+  cpu_baseline / --impl reference
+             the cheq-equivalent CPU path (oracle/: C pair integrals + LAPACK partial-pivot LU, one fresh
+             factorisation per SCF iteration exactly like the reference) timed on this box's host cores on a
+             bounded sample and extrapolated by pair count and LAPACK flop count (stated in `sample`).
+             cheq itself is Rust with un-vendored crates and cannot be built offline.
+
+N > 1 (torchrun): every rank solves its own replica of the workload (no data-path collective exists for one
+dense solve yet: "replicas only"); value = step time / N, i.e. job-level seconds per solve.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "qeq_solve_time_n20k_sto_fp64"
+UNIT = "s"
+# SCF iterations of the S20k workload (seed 20261019) as executed by the GPU path and by the pivoted-LU path
+# (identical trajectories); used to extrapolate the CPU arm, which cannot run 18 full 20k LUs in minutes.
+KNOWN_ITERATIONS = {"s20k": 18}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--molecules", type=int, default=6667, help="waters in the cluster (6667 = S20k)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload(molecules: int, rank: int = 0):
+    from cheq_b200 import get_default_parameters, workloads
+    Z, xyz = workloads.water_cluster(molecules, workloads.SEED + rank)
+    chi, hard, rad, nq = workloads.gather_parameters(Z, get_default_parameters())
+    name = "S20k" if molecules == 6667 else f"W{3 * molecules}"
+    return name, Z, np.ascontiguousarray(xyz), chi, hard, rad, nq
+
+
+# ---- CPU arm ------------------------------------------------------------------------------------------------
+def cpu_reference_sample(Z, xyz, iterations: int, budget_s: float):
+    """One bounded sample of the cheq-equivalent CPU path -> extrapolated seconds per full solve."""
+    from scipy.linalg import lu_factor, lu_solve
+
+    from oracle import oracle as O
+    P = O.default_parameters()
+    n = len(Z)
+    cores = O.num_threads()
+    opt = O.Options()
+    # probes
+    chi, hard, rad, nq = O.gather(Z[:600], P)
+    O.build_system(xyz[:600], chi, hard, rad, nq, 0.0, None, opt)                 # warms tables/threads
+    t0 = time.perf_counter()
+    O.build_system(xyz[:600], chi, hard, rad, nq, 0.0, None, opt)
+    t_pair = (time.perf_counter() - t0) / (600 * 599 / 2)
+    m = np.random.default_rng(0).normal(size=(2000, 2000)) + 50 * np.eye(2000)
+    t0 = time.perf_counter()
+    lu_factor(m, check_finite=False)
+    lu_rate = (2.0 / 3.0) * 2000 ** 3 / (time.perf_counter() - t0)
+    # sample sizes from the budget: ~35 % assembly, ~65 % LU
+    n_a = int(min(n, max(1000, (2 * 0.35 * budget_s / t_pair) ** 0.5)))
+    n_l = int(min(n + 1, max(2000, (0.65 * budget_s * lu_rate * 1.5) ** (1.0 / 3.0))))
+    chi, hard, rad, nq = O.gather(Z[:n_a], P)
+    t0 = time.perf_counter()
+    M, rhs, hidx = O.build_system(xyz[:n_a], chi, hard, rad, nq, 0.0, None, opt)
+    t_asm = time.perf_counter() - t0
+    t_asm_full = t_asm * (n * (n - 1.0)) / (n_a * (n_a - 1.0))
+    if n_l > n_a + 1:   # LU operand: any well-conditioned matrix of the right size costs the same flops
+        W = np.random.default_rng(1).normal(size=(n_l, n_l))
+        W += n_l * np.eye(n_l)
+        W = np.asfortranarray(W)
+        b = np.ones(n_l)
+    else:
+        W = np.asfortranarray(M[:n_l, :n_l])
+        b = rhs[:n_l]
+    t0 = time.perf_counter()
+    lu, piv = lu_factor(W, overwrite_a=False, check_finite=False)
+    lu_solve((lu, piv), b, check_finite=False)
+    t_lu = time.perf_counter() - t0
+    t_lu_full = t_lu * ((n + 1.0) / n_l) ** 3
+    total = t_asm_full + iterations * t_lu_full
+    sample = (f"assembly of a {n_a}-atom sub-cluster ({t_asm:.2f} s, scaled by pair count to N={n}: {t_asm_full:.1f} s) + "
+              f"one LAPACK dgetrf+dgetrs of order {n_l} ({t_lu:.2f} s, scaled by (N+1)^3 to {t_lu_full:.1f} s) x "
+              f"{iterations} SCF iterations (one fresh LU per iteration as in implementation.rs:303-314); "
+              f"cheq-equivalent CPU path (restated; faer/sto-ns not available offline)")
+    return total, sample, cores
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    name, Z, xyz, *_ = workload(args.molecules)
+    its = KNOWN_ITERATIONS.get(name.lower(), 10)
+    per_step = min(25.0, 150.0 / max(1, args.steps + args.warmup))
+    for _ in range(args.warmup):
+        cpu_reference_sample(Z, xyz, its, per_step)
+    vals = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, sample, cores = cpu_reference_sample(Z, xyz, its, per_step)
+        vals.append(v)
+    wall = time.perf_counter() - t0
+    value = float(np.median(vals))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / max(1, args.steps) * 1e3,
+        "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{name}: {len(Z)}-atom open water cluster, STO, hydrogen SCF, total charge 0",
+                   "note": "value is extrapolated from a bounded sample per step (see cpu_baseline.sample); "
+                           "ms_per_step is the wall time of one sample"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ---- GPU arm ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [c.strip() for c in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measure_fp64_peak(torch, device):
+    """cuBLAS DGEMM 8192^3, best of 10 and a 2 s sustained loop (same protocol as MEASURED_PEAKS.json's bf16 entry)."""
+    n = 8192
+    a = torch.randn(n, n, dtype=torch.float64, device=device)
+    b = torch.randn(n, n, dtype=torch.float64, device=device)
+    torch.matmul(a, b)
+    torch.cuda.synchronize()
+    best = 0.0
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 0
+    e0.record()
+    t0 = time.perf_counter()
+    while time.perf_counter() - t0 < 2.0:
+        torch.matmul(a, b)
+        reps += 1
+        if reps % 4 == 0:
+            torch.cuda.synchronize()
+    e1.record()
+    torch.cuda.synchronize()
+    sustained = reps * 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    del a, b
+    return best, sustained
+
+
+def run_ours(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    import cheq_b200
+    from cheq_b200 import QEqSolver, SolverOptions, _ffi, get_default_parameters
+    from cheq_b200.solver import make_options, raise_for_status
+
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    name, Z, xyz, chi, hard, rad, nq = workload(args.molecules, rank)
+    n = len(Z)
+    ctx = cheq_b200.Context(local_rank)
+    lib = ctx._lib
+    opt = make_options(SolverOptions())
+    stream = torch.cuda.ExternalStream(lib.cheq_ctx_stream(ctx.handle), device=device)
+
+    d_xyz = torch.from_numpy(xyz).to(device)
+    d_chi = torch.from_numpy(chi).to(device)
+    d_hard = torch.from_numpy(hard).to(device)
+    d_rad = torch.from_numpy(rad).to(device)
+    d_nq = torch.from_numpy(nq).to(device)
+    d_q = torch.empty(n, dtype=torch.float64, device=device)
+    pot, its, delta = C.c_double(), C.c_uint32(), C.c_double()
+    torch.cuda.synchronize()
+
+    def step_device():
+        rc = lib.cheq_solve_device(ctx.handle, n, d_xyz.data_ptr(), d_chi.data_ptr(), d_hard.data_ptr(),
+                                   d_rad.data_ptr(), d_nq.data_ptr(), 0.0, C.byref(opt), None, d_q.data_ptr(),
+                                   C.byref(pot), C.byref(its), C.byref(delta))
+        raise_for_status(ctx, rc, opt.max_iterations, delta.value)
+
+    # pinned host buffers for the end-to-end path
+    h_xyz = torch.from_numpy(xyz).pin_memory()
+    h_chi = torch.from_numpy(chi).pin_memory()
+    h_hard = torch.from_numpy(hard).pin_memory()
+    h_q = torch.empty(n, dtype=torch.float64).pin_memory()
+
+    def step_host():
+        rc = lib.cheq_solve(ctx.handle, n, h_xyz.data_ptr(), h_chi.data_ptr(), h_hard.data_ptr(),
+                            rad.ctypes.data_as(C.c_void_p), nq.ctypes.data_as(C.c_void_p), 0.0, C.byref(opt), None,
+                            h_q.data_ptr(), C.byref(pot), C.byref(its), C.byref(delta))
+        raise_for_status(ctx, rc, opt.max_iterations, delta.value)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=device)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    lib.cheq_set_profiling(ctx.handle, 1)
+    for _ in range(args.warmup):
+        step_device()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    gemm_ms = gemm_fl = 0.0
+    gemm_n = launches = 0
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device()
+        st = ctx.stats()
+        gemm_ms += st["gemm_ms"]
+        gemm_fl += st["gemm_flops"]
+        gemm_n += st["gemm_launches"]
+        launches += st["kernel_launches"]
+    e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    ms_t = torch.tensor([e0.elapsed_time(e1)], device=device)
+    if world > 1:
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_total = float(ms_t.item())
+    stats = ctx.stats()
+    iterations = int(its.value)
+    mu_dev = pot.value
+    q_dev = d_q.cpu().numpy()
+
+    lib.cheq_set_profiling(ctx.handle, 0)
+    for _ in range(min(args.warmup, 1)):
+        step_host()
+    ms_e2e = timed(step_host, args.steps)
+    assert abs(pot.value - mu_dev) < 1e-9 and np.max(np.abs(h_q.numpy() - q_dev)) < 1e-9
+
+    launches_t = torch.tensor([float(launches)], device=device)
+    if world > 1:
+        dist.all_reduce(launches_t)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    ms_per_step = ms_total / args.steps
+    value = ms_per_step / 1e3 / world
+    e2e_value = ms_e2e / args.steps / 1e3 / world
+    peak_burst, peak_sustained = measure_fp64_peak(torch, device)
+    achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    hbm_peak = None
+    try:
+        hbm_peak = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()).get("hbm_gbs")
+    except Exception:
+        pass
+    asm_gbs = stats["bytes_assemble"] / (stats["ms_assemble"] * 1e-3) / 1e9 if stats["ms_assemble"] > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{name}: {n}-atom open water cluster (seed {20261019}), STO, hydrogen SCF "
+                               f"({iterations} iterations), total charge 0, default SolverOptions",
+                   "parallelism": "replicas only" if world > 1 else "single GPU",
+                   "l2": "working set (3.3 GB matrix) >> 126 MB L2; no flush needed",
+                   "phases_ms": {k: stats[k] for k in ("ms_host_prepare", "ms_h2d", "ms_assemble", "ms_factor_once",
+                                                       "ms_scf", "ms_d2h")},
+                   "factor_tflops_overall": stats["flops_factor"] / ((stats["ms_factor_once"] + stats["ms_scf"]) * 1e9),
+                   "lu_fallback_frames": stats["lu_fallback_frames"]},
+        "roofline": {"bound": "tensor", "kernel": "gemm_nt_kernel (FP64 DMMA.8x8x4)", "achieved": achieved,
+                     "peak": peak_sustained, "unit": "TFLOP/s", "frac": achieved / peak_sustained if peak_sustained else None,
+                     "traffic": None, "launches": gemm_n, "kernel_ms_per_step": gemm_ms / args.steps,
+                     "share_of_step": gemm_ms / ms_total,
+                     "peak_source": f"cuBLAS DGEMM 8192^3 measured in this run: sustained {peak_sustained:.1f}, "
+                                    f"burst {peak_burst:.1f} TFLOP/s (MEASURED_PEAKS.json has no fp64 entry)"},
+        "roofline_assembly": {"bound": "hbm", "kernel": "assemble_lower_kernel<STO>", "achieved": asm_gbs,
+                              "peak": hbm_peak, "unit": "GB/s", "frac": asm_gbs / hbm_peak if hbm_peak else None,
+                              "traffic": None, "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * (24 + 8 + 8)),
+                "d2h_bytes_per_step": int(n * 8 + 64)},
+        "gpu_launches": int(launches_t.item()),
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        v, sample, cores = cpu_reference_sample(Z, xyz, iterations, 20.0)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

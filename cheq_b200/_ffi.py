@@ -27,7 +27,8 @@ class Stats(C.Structure):
                 ("ms_d2h", C.c_double), ("kernel_launches", C.c_uint64), ("n_atoms", C.c_uint64),
                 ("n_hydrogen", C.c_uint64), ("n_padded", C.c_uint64), ("iterations", C.c_uint32),
                 ("pair_types", C.c_uint32), ("flops_factor", C.c_double), ("bytes_assemble", C.c_double),
-                ("lu_fallback_frames", C.c_uint64)]
+                ("lu_fallback_frames", C.c_uint64), ("gemm_ms", C.c_double), ("gemm_flops", C.c_double),
+                ("gemm_launches", C.c_uint64)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -42,6 +43,7 @@ SIGNATURES = {
     "cheq_options_default": (None, [C.POINTER(Options)]),
     "cheq_get_stats": (_I32, [_P, C.POINTER(Stats)]),
     "cheq_ctx_stream": (_P, [_P]),
+    "cheq_set_profiling": (_I32, [_P, _I32]),
     "cheq_solve": (_I32, [_P, _U64, _P, _P, _P, _P, _P, _D, C.POINTER(Options), C.POINTER(External), _P,
                           C.POINTER(_D), C.POINTER(C.c_uint32), C.POINTER(_D)]),
     "cheq_solve_device": (_I32, [_P, _U64, _P, _P, _P, _P, _P, _D, C.POINTER(Options), C.POINTER(External), _P,

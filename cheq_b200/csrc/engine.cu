@@ -108,6 +108,11 @@ struct cheq_ctx {
     size_t h_state_cap = 0;
     cudaEvent_t ev[8]{};
     uint64_t launches = 0;
+    // optional per-launch timing of the dominant kernel (gemm_nt_kernel) with CUDA events on the stream
+    bool profile = false;
+    std::vector<cudaEvent_t> prof_events;   // pairs (start, stop)
+    size_t prof_used = 0;
+    double prof_flops = 0.0;
 };
 
 namespace {
@@ -343,6 +348,24 @@ struct Dense {
 // Matrix entries are O(1..30) eV, so accepted pivots bound the element growth by ~1e5 (error ~1e-11).
 constexpr double kPivotTol = 1.0e-4;
 
+int launch_gemm_timed(cheq_ctx* ctx, const GemmArgs& g, int mt, int nt, int batch, double flops) {
+    if (!ctx->profile) {
+        LAUNCH(launch_gemm_nt(g, mt, nt, batch, ctx->stream));
+        return CHEQ_OK;
+    }
+    if (ctx->prof_used + 2 > ctx->prof_events.size()) {
+        const size_t old = ctx->prof_events.size();
+        ctx->prof_events.resize(old + 4096, nullptr);
+        for (size_t i = old; i < ctx->prof_events.size(); ++i) CU(cudaEventCreate(&ctx->prof_events[i]));
+    }
+    CU(cudaEventRecord(ctx->prof_events[ctx->prof_used], ctx->stream));
+    LAUNCH(launch_gemm_nt(g, mt, nt, batch, ctx->stream));
+    CU(cudaEventRecord(ctx->prof_events[ctx->prof_used + 1], ctx->stream));
+    ctx->prof_used += 2;
+    ctx->prof_flops += flops * batch;
+    return CHEQ_OK;
+}
+
 // Recursive tall-panel Cholesky of columns [j0, j0 + n) with all rows down to MT (the rows below the panel are
 // overwritten by A L^-T, i.e. the triangular solve is part of every leaf).
 int factor_panel(Dense& D, int j0, int n) {
@@ -369,7 +392,8 @@ int factor_panel(Dense& D, int j0, int n) {
             g.lower = 0;
             g.subtract = 0;
             g.state = D.state;
-            LAUNCH(launch_gemm_nt(g, mt, 1, D.batch, ctx->stream));
+            const int rc2 = launch_gemm_timed(ctx, g, mt, 1, D.batch, 2.0 * mt * kTile * (double)kTile * kTile);
+            if (rc2) return rc2;
         }
         const double m = (double)(D.MT - j0 - kTile);
         D.flops += (double)kTile * kTile * kTile / 3.0 + m * kTile * kTile;
@@ -397,9 +421,11 @@ int factor_panel(Dense& D, int j0, int n) {
         g.strideSgn = D.strideSgn;
         g.state = D.state;
         const int mt = (D.MT - r0) / kTile, nt = (n - n1) / kTile;
-        LAUNCH(launch_gemm_nt(g, mt, nt, D.batch, ctx->stream));
         const double w = (double)(n - n1), m = (double)(D.MT - r0);
-        D.flops += (double)n1 * (w * w + 2.0 * (m - w) * w);   // syrk on the square part + gemm below it
+        const double fl = (double)n1 * (w * w + 2.0 * (m - w) * w);   // syrk on the square part + gemm below it
+        const int rc2 = launch_gemm_timed(ctx, g, mt, nt, D.batch, fl);
+        if (rc2) return rc2;
+        D.flops += fl;
     }
     return factor_panel(D, j0 + n1, n - n1);
 }
@@ -424,9 +450,11 @@ int schur_update(Dense& D, int k, int ncols) {
     g.sgn = D.sgn;
     g.strideSgn = D.strideSgn;
     g.state = D.state;
-    LAUNCH(launch_gemm_nt(g, (D.MT - k) / kTile, ncols / kTile, D.batch, ctx->stream));
     const double w = (double)ncols, m = (double)(D.MT - k);
-    D.flops += (double)k * (w * w + 2.0 * (m - w) * w);
+    const double fl = (double)k * (w * w + 2.0 * (m - w) * w);
+    const int rc2 = launch_gemm_timed(ctx, g, (D.MT - k) / kTile, ncols / kTile, D.batch, fl);
+    if (rc2) return rc2;
+    D.flops += fl;
     return CHEQ_OK;
 }
 
@@ -846,6 +874,8 @@ int solve_impl(cheq_ctx* ctx, const SolveIO& io) {
     ctx->err.clear();
     ctx->stats = cheq_stats{};
     ctx->launches = 0;
+    ctx->prof_used = 0;
+    ctx->prof_flops = 0.0;
     if (io.n == 0) return fail(ctx, CHEQ_ERR_NO_ATOMS, "Input validation failed: at least one atom is required for a calculation");
     int rc = validate_options(ctx, io.opt);
     if (rc) return rc;
@@ -918,6 +948,17 @@ int solve_impl(cheq_ctx* ctx, const SolveIO& io) {
         }
     }
     ctx->stats.kernel_launches = ctx->launches;
+    if (ctx->profile) {
+        double ms_sum = 0.0;
+        for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, ctx->prof_events[i], ctx->prof_events[i + 1]);
+            ms_sum += ms;
+        }
+        ctx->stats.gemm_ms = ms_sum;
+        ctx->stats.gemm_launches = ctx->prof_used / 2;
+        ctx->stats.gemm_flops = ctx->prof_flops;
+    }
     ctx->stats.ms_total = ms_since(t_total);
     if (io.frames > 1 && io.status_out) return CHEQ_OK;
     return worst;
@@ -967,6 +1008,8 @@ void cheq_ctx_destroy(cheq_ctx* ctx) {
     if (ctx->h_active) cudaFreeHost(ctx->h_active);
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
+    for (auto& e : ctx->prof_events)
+        if (e) cudaEventDestroy(e);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -993,6 +1036,13 @@ int32_t cheq_get_stats(const cheq_ctx* ctx, cheq_stats* out) {
 }
 
 void* cheq_ctx_stream(const cheq_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int32_t cheq_set_profiling(cheq_ctx* ctx, int32_t enabled) {
+    if (!ctx) return CHEQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->profile = enabled != 0;
+    return CHEQ_OK;
+}
 
 int32_t cheq_solve(cheq_ctx* ctx, uint64_t n_atoms, const double* xyz, const double* chi, const double* hardness,
                    const double* radius, const uint8_t* n_quantum, double total_charge, const cheq_options* options,

@@ -83,7 +83,11 @@ typedef struct cheq_stats {
     uint32_t pair_types;
     double flops_factor;     /* LAPACK-count flops of the factorisation work actually performed */
     double bytes_assemble;   /* algorithmic bytes of the assembly: 8 * N (N + 1) / 2 */
-    uint64_t lu_fallback_frames; /* frames re-solved with the pivoted-LU path (matrix not positive definite) */
+    uint64_t lu_fallback_frames; /* frames re-solved with the pivoted-LU path (unpivoted factorisation broke down) */
+    /* filled only when cheq_set_profiling(ctx, 1): every launch of the tensor-core GEMM bracketed by CUDA events */
+    double gemm_ms;          /* sum of the launch durations */
+    double gemm_flops;       /* algorithmic flops of those launches (2 m n k; n^2 k for the symmetric part) */
+    uint64_t gemm_launches;
 } cheq_stats;
 
 int32_t cheq_ctx_create(int32_t device, cheq_ctx** out);
@@ -93,6 +97,8 @@ void cheq_options_default(cheq_options* opt);
 int32_t cheq_get_stats(const cheq_ctx* ctx, cheq_stats* out);
 /* The context's CUDA stream as a cudaStream_t cast to void* (for callers that time with events). */
 void* cheq_ctx_stream(const cheq_ctx* ctx);
+/* Per-launch CUDA-event timing of the dominant kernel (off by default; adds two event records per launch). */
+int32_t cheq_set_profiling(cheq_ctx* ctx, int32_t enabled);
 
 /*
  * QEqSolver::solve / solve_in_field after element lookup.  `external` may be NULL or empty
