@@ -102,7 +102,7 @@ struct cheq_ctx {
     // device workspace (grow-only)
     DeviceBuffer in_xyz, in_chi, in_hard, in_radius, in_nq, perm, type, x, y, z, diag, chi, hard, vext, A, S0,
         Linv, v, q, scratch, counters, state, active, blob, pc_xyz, pc_q, pc_type, out_q, misc0, misc1, misc2,
-        lu_f, lu_piv, sgn;
+        lu_f, lu_piv, sgn, sgn_flags;
     ScfState* h_state = nullptr;   // pinned
     int* h_active = nullptr;       // pinned
     size_t h_state_cap = 0;
@@ -341,6 +341,9 @@ struct Dense {
     int batch;
     double* sgn;        // [batch][NP] pivot signs of A = L S L^T
     long strideSgn;
+    int* neg_cnt;       // [batch][NP / 128] number of negative pivots per tile
+    int* neg_idx;       // [batch][NP / 128][128] their in-tile indices
+    long strideNeg;
     double flops = 0.0;
 };
 
@@ -374,8 +377,8 @@ int factor_panel(Dense& D, int j0, int n) {
     if (n == kTile) {
         double* Ajj = D.A + (long)j0 + (long)j0 * D.ld;
         double* Lk = D.Linv + (long)(j0 / kTile) * kTile * kTile;
-        LAUNCH(launch_potrf_tile(Ajj, D.ld, D.strideA, Lk, D.strideLinv, D.sgn + j0, D.strideSgn, D.state, kPivotTol,
-                                 D.batch, ctx->stream));
+        LAUNCH(launch_potrf_tile(Ajj, D.ld, D.strideA, Lk, D.strideLinv, D.sgn + j0, D.strideSgn, D.neg_cnt + j0 / kTile,
+                                 D.neg_idx + (long)j0, D.strideNeg, D.state, kPivotTol, D.batch, ctx->stream));
         const int mt = (D.MT - j0 - kTile) / kTile;
         if (mt > 0) {
             GemmArgs g{};
@@ -417,8 +420,9 @@ int factor_panel(Dense& D, int j0, int n) {
         g.K = n1;
         g.lower = 1;
         g.subtract = 1;
-        g.sgn = D.sgn + j0;
-        g.strideSgn = D.strideSgn;
+        g.neg_cnt = D.neg_cnt + j0 / kTile;
+        g.neg_idx = D.neg_idx + (long)j0;
+        g.strideNeg = D.strideNeg;
         g.state = D.state;
         const int mt = (D.MT - r0) / kTile, nt = (n - n1) / kTile;
         const double w = (double)(n - n1), m = (double)(D.MT - r0);
@@ -447,8 +451,9 @@ int schur_update(Dense& D, int k, int ncols) {
     g.K = k;
     g.lower = 1;
     g.subtract = 1;
-    g.sgn = D.sgn;
-    g.strideSgn = D.strideSgn;
+    g.neg_cnt = D.neg_cnt;
+    g.neg_idx = D.neg_idx;
+    g.strideNeg = D.strideNeg;
     g.state = D.state;
     const double w = (double)ncols, m = (double)(D.MT - k);
     const double fl = (double)k * (w * w + 2.0 * (m - w) * w);
@@ -602,6 +607,7 @@ int prepare_and_assemble(cheq_ctx* ctx, const SolveIO& io, long frame0, int batc
     CU(ctx->scratch.ensure((size_t)backsolve_max_ctas() * kTile * 8 * batch));
     CU(ctx->counters.ensure(sizeof(unsigned) * batch));
     CU(ctx->sgn.ensure(vec));
+    CU(ctx->sgn_flags.ensure((size_t)(L.NP / kTile) * (kTile + 1) * sizeof(int) * batch));   // counts, then lists
     CU(ctx->state.ensure(sizeof(ScfState) * batch));
     CU(ctx->active.ensure(sizeof(int)));
     int rc = ensure_host_state(ctx, batch);
@@ -707,7 +713,8 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
     cudaStream_t st = ctx->stream;
     const int batch = P.batch;
     Dense D{ctx, ctx->A.as<double>(), L.ld, P.strideA, ctx->Linv.as<double>(), (long)L.NP * kTile, L.MT,
-            ctx->state.as<ScfState>(), batch, ctx->sgn.as<double>(), (long)L.NP};
+            ctx->state.as<ScfState>(), batch, ctx->sgn.as<double>(), (long)L.NP, ctx->sgn_flags.as<int>(),
+            ctx->sgn_flags.as<int>() + (size_t)(L.NP / kTile) * batch, (long)L.NP / kTile};
     double damping0 = 1.0;   // implementation.rs:297-301
     if (L.scf && o.damping_kind != CHEQ_DAMPING_NONE) damping0 = o.damping_value;
     LAUNCH(launch_scf_init(ctx->state.as<ScfState>(), damping0, batch, st));
@@ -1002,7 +1009,7 @@ void cheq_ctx_destroy(cheq_ctx* ctx) {
                             &ctx->type, &ctx->x, &ctx->y, &ctx->z, &ctx->diag, &ctx->chi, &ctx->hard, &ctx->vext,
                             &ctx->A, &ctx->S0, &ctx->Linv, &ctx->v, &ctx->q, &ctx->scratch, &ctx->counters,
                             &ctx->state, &ctx->active, &ctx->blob, &ctx->pc_xyz, &ctx->pc_q, &ctx->pc_type,
-                            &ctx->out_q, &ctx->misc0, &ctx->misc1, &ctx->misc2, &ctx->lu_f, &ctx->lu_piv, &ctx->sgn};
+                            &ctx->out_q, &ctx->misc0, &ctx->misc1, &ctx->misc2, &ctx->lu_f, &ctx->lu_piv, &ctx->sgn, &ctx->sgn_flags};
     for (DeviceBuffer* b : bufs) b->release();
     if (ctx->h_state) cudaFreeHost(ctx->h_state);
     if (ctx->h_active) cudaFreeHost(ctx->h_active);
@@ -1300,8 +1307,10 @@ int32_t cheq_dbg_cholesky_solve(cheq_ctx* ctx, uint64_t n_, const double* a, uin
     CU(cudaMemcpyAsync(ctx->A.p, h.data(), h.size() * 8, cudaMemcpyHostToDevice, st));
     LAUNCH(launch_scf_init(ctx->state.as<ScfState>(), 1.0, 1, st));
     CU(ctx->sgn.ensure(NP * 8));
+    CU(ctx->sgn_flags.ensure((size_t)(NP / kTile) * (kTile + 1) * sizeof(int)));
     Dense D{ctx, ctx->A.as<double>(), ld, (long)ld * NP, ctx->Linv.as<double>(), (long)NP * kTile, MT,
-            ctx->state.as<ScfState>(), 1, ctx->sgn.as<double>(), (long)NP};
+            ctx->state.as<ScfState>(), 1, ctx->sgn.as<double>(), (long)NP, ctx->sgn_flags.as<int>(),
+            ctx->sgn_flags.as<int>() + NP / kTile, (long)NP / kTile};
     rc = factor_panel(D, 0, NP);
     if (rc) return rc;
     std::vector<double> xv(NP);
@@ -1324,6 +1333,42 @@ int32_t cheq_dbg_cholesky_solve(cheq_ctx* ctx, uint64_t n_, const double* a, uin
     CU(cudaStreamSynchronize(st));
     ctx->stats.kernel_launches = ctx->launches;
     if (ctx->h_state[0].info != 0) return fail(ctx, CHEQ_ERR_LINALG, "matrix is not positive definite");
+    return CHEQ_OK;
+}
+
+int32_t cheq_dbg_gemm_bench(cheq_ctx* ctx, uint64_t m, uint64_t n, uint64_t k, int32_t lower, int32_t subtract,
+                            int32_t reps, double* ms_out) {
+    if (!ctx || !ms_out) return CHEQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->err.clear();
+    if (m % kTile || n % kTile || k % kTile || !m || !n || !k || reps < 1)
+        return fail(ctx, CHEQ_ERR_INVALID_ARGUMENT, "m, n, k must be positive multiples of 128");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CU(ctx->misc0.ensure(m * k * 8));
+    CU(ctx->misc1.ensure(n * k * 8));
+    CU(ctx->misc2.ensure(m * n * 8));
+    CU(cudaMemsetAsync(ctx->misc0.p, 0x3f, m * k * 8, st));   // every double = 0.000473...
+    CU(cudaMemsetAsync(ctx->misc1.p, 0x3f, n * k * 8, st));
+    CU(cudaMemsetAsync(ctx->misc2.p, 0x3f, m * n * 8, st));
+    GemmArgs g{};
+    g.A = ctx->misc0.as<double>();
+    g.lda = (long)m;
+    g.B = ctx->misc1.as<double>();
+    g.ldb = (long)n;
+    g.C = ctx->misc2.as<double>();
+    g.ldc = (long)m;
+    g.K = (int)k;
+    g.lower = lower & 1;
+    g.subtract = subtract ? 1 : 0;
+    LAUNCH(launch_gemm_nt(g, (int)(m / kTile), (int)(n / kTile), 1, st));   // warm-up
+    CU(cudaEventRecord(ctx->ev[0], st));
+    for (int r = 0; r < reps; ++r) LAUNCH(launch_gemm_nt(g, (int)(m / kTile), (int)(n / kTile), 1, st));
+    CU(cudaEventRecord(ctx->ev[1], st));
+    CU(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    *ms_out = ms / reps;
     return CHEQ_OK;
 }
 

@@ -48,8 +48,12 @@ struct GemmArgs {
     int K;
     int lower;                 // 1: skip tiles strictly above the diagonal of C
     int subtract;              // 1: C -= A S B^T ; 0: C = A S B^T (C may alias A when the grid has one tile column)
-    const double* sgn;         // nullable: S = diag(+-1) over the K range (pivot signs of A = L S L^T)
-    long strideSgn;
+    // nullable: negative pivots of the K range, per 128-column tile of K (first tile of the range at index 0):
+    // neg_cnt[tile] entries of neg_idx[tile * 128 ...] are the in-tile column indices with pivot sign -1
+    const int* neg_cnt;
+    const int* neg_idx;
+    long strideNeg;            // per frame, in tiles
+    int m_tiles, n_tiles;      // filled by the launcher
     const ScfState* state;     // nullable; frames with active == 0 are skipped
 };
 
@@ -73,7 +77,8 @@ cudaError_t launch_gemm_nt(const GemmArgs& g, int m_tiles, int n_tiles, int batc
 // A = L S L^T of one 128 x 128 diagonal block in place (lower) + M = S L^-1 (dense 128 x 128, ld 128) + the signs.
 // |pivot| <= pivot_tol sets state.info (the caller then falls back to the pivoted LU).
 cudaError_t launch_potrf_tile(double* A, long lda, long strideA, double* Linv, long strideLinv, double* sgn,
-                              long strideSgn, ScfState* state, double pivot_tol, int batch, cudaStream_t stream);
+                              long strideSgn, int* neg_cnt, int* neg_idx, long strideNeg, ScfState* state,
+                              double pivot_tol, int batch, cudaStream_t stream);
 // copies the tiles on/below the diagonal of an (m_tiles x n_tiles) tile region
 cudaError_t launch_copy_lower_tiles(const double* src, long lds, long stride_src, double* dst, long ldd,
                                     long stride_dst, int m_tiles, int n_tiles, const ScfState* state, int batch,

@@ -29,6 +29,10 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
 }
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -41,15 +45,35 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
                  : "d"(a), "d"(b));
 }
 
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
+}
+
+constexpr int kGroupM = 8;   // tile rows per rasterisation group: their A slabs stay in L2 while B streams
+
+// C (-)= A S B^T with S = diag(+-1) over K (pivot signs of A = L S L^T).  The main loop ignores S (measured:
+// scaling B fragments in the loop costs 4 % of DMMA throughput, a flagged branch 11 %); negative pivots are rare
+// (one per negative eigenvalue), so the epilogue applies  A S B^T = A B^T - 2 sum_{k: s_k = -1} a_k b_k^T  as
+// rank-1 corrections to the accumulators, driven by the per-tile lists the factorisation leaf writes.
 __global__ void __launch_bounds__(kGemmThreads, 1) gemm_nt_kernel(GemmArgs g) {
-    const int tile_m = blockIdx.x, tile_n = blockIdx.y, frame = blockIdx.z;
+    // grouped rasterisation: consecutive CTAs walk the tile columns of a group of kGroupM tile rows
+    const int frame = blockIdx.z;
+    int tile_m, tile_n;
+    {
+        const int pid = blockIdx.x;
+        const int per_group = kGroupM * g.n_tiles;
+        const int group = pid / per_group, rem = pid - group * per_group;
+        const int first = group * kGroupM;
+        const int gsize = min(kGroupM, g.m_tiles - first);
+        tile_n = rem / gsize;
+        tile_m = first + (rem - tile_n * gsize);
+    }
     if (g.lower && tile_m < tile_n) return;
     if (g.state && !g.state[frame].active) return;
     extern __shared__ __align__(16) double smem[];
     double* As = smem;                          // [STAGES][BK][LDT]
     double* Bs = smem + STAGES * BK * LDT;      // [STAGES][BK][LDT]
-    __shared__ double sgs[STAGES][BK];          // pivot signs of the K range (A = L S L^T), 1 if absent
-    const double* sgn = g.sgn ? g.sgn + (long)frame * g.strideSgn : nullptr;
 
     const double* A = g.A + (long)frame * g.strideA + (long)tile_m * BM;
     const double* B = g.B + (long)frame * g.strideB + (long)tile_n * BN;
@@ -70,7 +94,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_nt_kernel(GemmArgs g) {
             cp_async16(as + kr * LDT + 2 * mc, A + 2 * mc + (k0 + kr) * g.lda);
             cp_async16(bs + kr * LDT + 2 * mc, B + 2 * mc + (k0 + kr) * g.ldb);
         }
-        if (t < BK) sgs[stage][t] = sgn ? sgn[k0 + t] : 1.0;
     };
 
     double acc[4][2][2][2][2];  // [fm][row parity][fn][col parity][e]
@@ -92,8 +115,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_nt_kernel(GemmArgs g) {
             if (nxt < kt) load_stage(nxt % STAGES, nxt);
             cp_async_commit();
         }
-        const double* as = As + (it % STAGES) * BK * LDT + wm * 64 + 2 * gq;
-        const double* bs = Bs + (it % STAGES) * BK * LDT + wn * 32 + 2 * gq;
+        const int stage = it % STAGES;
+        const double* as = As + stage * BK * LDT + wm * 64 + 2 * gq;
+        const double* bs = Bs + stage * BK * LDT + wn * 32 + 2 * gq;
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
             double2 a[4], b[2];
@@ -101,12 +125,6 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_nt_kernel(GemmArgs g) {
             for (int fm = 0; fm < 4; ++fm) a[fm] = *(const double2*)(as + (kk * 4 + q) * LDT + fm * 16);
 #pragma unroll
             for (int fn = 0; fn < 2; ++fn) b[fn] = *(const double2*)(bs + (kk * 4 + q) * LDT + fn * 16);
-            const double sv = sgs[it % STAGES][kk * 4 + q];
-#pragma unroll
-            for (int fn = 0; fn < 2; ++fn) {
-                b[fn].x *= sv;
-                b[fn].y *= sv;
-            }
 #pragma unroll
             for (int fm = 0; fm < 4; ++fm)
 #pragma unroll
@@ -119,6 +137,40 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_nt_kernel(GemmArgs g) {
         }
     }
     cp_async_wait<0>();
+
+    // negative pivots inside the K range: acc -= 2 a_k b_k^T
+    if (g.neg_cnt) {
+        const int* cnt = g.neg_cnt + (long)frame * g.strideNeg;
+        const int* idx = g.neg_idx + (long)frame * g.strideNeg * kTile;
+        for (int kt128 = 0; kt128 < g.K / kTile; ++kt128) {
+            const int nneg = cnt[kt128];
+            for (int j = 0; j < nneg; ++j) {
+                const long k = (long)kt128 * kTile + idx[kt128 * kTile + j];
+                const double* ak = A + k * g.lda + wm * 64 + 2 * gq;
+                const double* bk = B + k * g.ldb + wn * 32 + 4 * q;
+                double2 av[4];
+                double bv[2][2][2];   // [fn][pc][e]: column 4 q + 2 e + pc of the 16-column group
+#pragma unroll
+                for (int fm = 0; fm < 4; ++fm) av[fm] = *(const double2*)(ak + fm * 16);
+#pragma unroll
+                for (int fn = 0; fn < 2; ++fn) {
+                    const double2 lo = *(const double2*)(bk + fn * 16), hi = *(const double2*)(bk + fn * 16 + 2);
+                    bv[fn][0][0] = lo.x; bv[fn][1][0] = lo.y; bv[fn][0][1] = hi.x; bv[fn][1][1] = hi.y;
+                }
+#pragma unroll
+                for (int fm = 0; fm < 4; ++fm)
+#pragma unroll
+                    for (int fn = 0; fn < 2; ++fn)
+#pragma unroll
+                        for (int pc = 0; pc < 2; ++pc)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) {
+                                acc[fm][0][fn][pc][e] = fma(-2.0 * av[fm].x, bv[fn][pc][e], acc[fm][0][fn][pc][e]);
+                                acc[fm][1][fn][pc][e] = fma(-2.0 * av[fm].y, bv[fn][pc][e], acc[fm][1][fn][pc][e]);
+                            }
+            }
+        }
+    }
 
     // epilogue: thread owns rows (2 gq, 2 gq + 1) of each 16-row group and columns 4 q + 2 e + pc of each
     // 16-column group
@@ -161,7 +213,7 @@ constexpr int kPotrfSmem = kTile * kPotrfLd * (int)sizeof(double);
 
 __global__ void __launch_bounds__(kPotrfThreads)
 potrf_tile_kernel(double* A_, long lda, long strideA, double* Minv_, long strideM, double* sgn_, long strideSgn,
-                  ScfState* state, double pivot_tol) {
+                  int* neg_cnt_, int* neg_idx_, long strideNeg, ScfState* state, double pivot_tol) {
     const int frame = blockIdx.z;
     if (state && !state[frame].active) return;
     extern __shared__ __align__(16) double Ms[];   // staging of M for a coalesced store
@@ -182,6 +234,7 @@ potrf_tile_kernel(double* A_, long lda, long strideA, double* Minv_, long stride
             e[a][b] = (r >= c) ? A[r + (long)c * lda] : 0.0;
         }
 
+    const bool p_diag = ty >= tx;   // within a diagonal 16 x 16 sub-block: element on or below the diagonal
     int cur = 0;
 #pragma unroll
     for (int kb = 0; kb < 8; ++kb) {
@@ -193,45 +246,63 @@ potrf_tile_kernel(double* A_, long lda, long strideA, double* Minv_, long stride
                 const double ad = fabs(d);
                 const bool bad = !(ad > pivot_tol) || !(ad < 1.0e300);
                 const double sgnk = (d < 0.0) ? -1.0 : 1.0;
-                const double l = bad ? 1.0 : sqrt(ad);
-                const double il = 1.0 / l;
+                // 1/sqrt and sqrt from one rsqrt plus a Newton step (shorter dependent chain than sqrt + divide)
+                double il = bad ? 1.0 : rsqrt(ad);
+                double l = bad ? 1.0 : ad * il;
+                if (!bad) {
+                    const double res = fma(-l, l, ad);        // ad - l^2
+                    l = fma(0.5 * il, res, l);
+                    il = fma(fma(-l, il, 1.0), il, il);
+                }
                 const double sil = sgnk * il;
                 if (ty == kt) {
                     dinv[k] = il;
                     sg[k] = sgnk;
                     if (bad && state) atomicExch(&state[frame].info, k + 1);
                 }
+                // logical column k: rows r = ty + 16 a.  a < kb: row k of X (r < k); a > kb: L column (r > k);
+                // a == kb: decided by ty vs kt.
 #pragma unroll
                 for (int a = 0; a < 8; ++a) {
-                    const int r = ty + 16 * a;
                     const double v = e[a][kb];
-                    double u;
-                    if (r == k) {
-                        u = sil;
-                        e[a][kb] = l;
-                    } else {
-                        u = v * sil;
-                        e[a][kb] = (r > k) ? u : v * il;   // L column below the pivot / row k of X
+                    double u = v * sil, keep;
+                    if (a < kb) keep = v * il;
+                    else if (a > kb) keep = u;
+                    else {
+                        keep = (ty > kt) ? u : v * il;
+                        if (ty == kt) {
+                            u = sil;
+                            keep = l;
+                        }
                     }
-                    ubuf[cur][r] = u;
+                    e[a][kb] = keep;
+                    ubuf[cur][ty + 16 * a] = u;
                 }
             }
             __syncthreads();
             const double sk = sg[k];
+            const bool p_row = ty <= kt;    // rows of block kb that are <= k
+            const bool p_col = tx > kt;     // columns of block kb that are > k
             double su[8];
 #pragma unroll
             for (int a = 0; a < 8; ++a) su[a] = sk * ubuf[cur][ty + 16 * a];
 #pragma unroll
             for (int b = 0; b < 8; ++b) {
-                if (b < kb) continue;
-                const int c = tx + 16 * b;
-                if (c > k) {
-                    const double uc = ubuf[cur][c];
+                if (b < kb) continue;                 // columns <= k: finished
+                if (b == kb && !p_col) continue;      // same block, column <= k
+                const double uc = ubuf[cur][tx + 16 * b];
 #pragma unroll
-                    for (int a = 0; a < 8; ++a) {
-                        const int r = ty + 16 * a;
-                        if (r >= c || r <= k) e[a][b] = fma(-su[a], uc, e[a][b]);
-                    }
+                for (int a = 0; a < 8; ++a) {
+                    // update iff (r >= c) [L part] or (r <= k) [X part]; resolved per (a, b, kb) at compile time
+                    // except inside the diagonal sub-block (p_diag) and the pivot's row block (p_row)
+                    bool upd;
+                    if (a > b) upd = true;
+                    else if (a < kb) upd = true;
+                    else if (a == b && a == kb) upd = p_diag || p_row;
+                    else if (a == b) upd = p_diag;
+                    else if (a == kb) upd = p_row;
+                    else upd = false;
+                    if (upd) e[a][b] = fma(-su[a], uc, e[a][b]);
                 }
             }
             cur ^= 1;
@@ -259,6 +330,13 @@ potrf_tile_kernel(double* A_, long lda, long strideA, double* Minv_, long stride
         Minv[idx] = Ms[j * kPotrfLd + i];
     }
     if (t < kTile && sgn_) sgn_[(long)frame * strideSgn + t] = sg[t];
+    if (t == 0 && neg_cnt_) {   // compact list of this tile's negative pivots for the GEMM epilogues
+        int n = 0;
+        int* idx = neg_idx_ + (long)frame * strideNeg * kTile;
+        for (int i = 0; i < kTile; ++i)
+            if (sg[i] < 0.0) idx[n++] = i;
+        neg_cnt_[(long)frame * strideNeg] = n;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -335,11 +413,11 @@ mu_kernel(const double* A_, long lda, long strideA, int NP, double total_charge,
 }
 
 // Backward substitution L^T x = v, block row kb:  x_kb = L_kk^-T (v_kb - L[rows below, kb cols]^T x[rows below]),
-// with L_kk^-T t = M_kk^T (S t).  Each CTA reduces a 256-row slab of the panel (every warp keeps 4 columns x 2 row
-// groups in flight), writes its 128 partial sums, and the last CTA to finish adds them in fixed order and applies
-// the diagonal block.
-constexpr int kBackMaxCtas = 160;
-constexpr int kBackRows = 256;
+// with L_kk^-T t = M_kk^T (S t).  Each CTA reduces a slab of rows of the 128-column panel (each warp keeps
+// 4 columns x 2 row groups of loads in flight) and writes 128 partial sums; the last CTA to finish adds the
+// partials in a fixed order (deterministic) and applies the diagonal block.
+constexpr int kBackMaxCtas = 296;
+constexpr int kBackSlab = 1024;   // rows of x staged in shared memory per CTA (upper bound on the slab)
 __global__ void __launch_bounds__(256)
 backsolve_step_kernel(const double* A_, long lda, long strideA, const double* Minv_, long strideM,
                       const double* sgn_, long strideSgn, int NP, int kb, double* v_, long v_stride,
@@ -359,40 +437,45 @@ backsolve_step_kernel(const double* A_, long lda, long strideA, const double* Mi
     chunk = (chunk + 63) & ~63;
     const int r0 = r_lo + c * chunk;
     const int r1 = min(NP, r0 + chunk);
-    __shared__ double xs[kBackRows * 4];   // slab of x (chunk <= 1024 rows by construction of G)
+    __shared__ double xs[kBackSlab];
+    __shared__ double tv[kTile];
+    __shared__ double part[2][kTile];
+    __shared__ bool is_last;
     for (int r = r0 + t; r < r1; r += 256) xs[r - r0] = v[r];
     __syncthreads();
 
-    for (int cg = 0; cg < 4; ++cg) {
-        const int col = warp * 16 + cg * 4;
-        const double* L0 = A + (long)(kb * kTile + col) * lda;
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int r = r0 + lane;
-        for (; r + 32 < r1; r += 64) {
-            const double xa = xs[r - r0], xb = xs[r + 32 - r0];
-            const double a0 = L0[r], a1 = L0[r + lda], a2 = L0[r + 2 * lda], a3 = L0[r + 3 * lda];
-            const double b0 = L0[r + 32], b1 = L0[r + 32 + lda], b2 = L0[r + 32 + 2 * lda], b3 = L0[r + 32 + 3 * lda];
-            s0 = fma(a0, xa, s0); s1 = fma(a1, xa, s1); s2 = fma(a2, xa, s2); s3 = fma(a3, xa, s3);
-            s0 = fma(b0, xb, s0); s1 = fma(b1, xb, s1); s2 = fma(b2, xb, s2); s3 = fma(b3, xb, s3);
+    if (r0 < r1) {
+        for (int cg = 0; cg < 4; ++cg) {
+            const int col = warp * 16 + cg * 4;
+            const double* L0 = A + (long)(kb * kTile + col) * lda;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            int r = r0 + lane;
+            for (; r + 32 < r1; r += 64) {
+                const double xa = xs[r - r0], xb = xs[r + 32 - r0];
+                const double a0 = L0[r], a1 = L0[r + lda], a2 = L0[r + 2 * lda], a3 = L0[r + 3 * lda];
+                const double b0 = L0[r + 32], b1 = L0[r + 32 + lda], b2 = L0[r + 32 + 2 * lda], b3 = L0[r + 32 + 3 * lda];
+                s0 = fma(a0, xa, s0); s1 = fma(a1, xa, s1); s2 = fma(a2, xa, s2); s3 = fma(a3, xa, s3);
+                s0 = fma(b0, xb, s0); s1 = fma(b1, xb, s1); s2 = fma(b2, xb, s2); s3 = fma(b3, xb, s3);
+            }
+            for (; r < r1; r += 32) {
+                const double xa = xs[r - r0];
+                s0 = fma(L0[r], xa, s0); s1 = fma(L0[r + lda], xa, s1);
+                s2 = fma(L0[r + 2 * lda], xa, s2); s3 = fma(L0[r + 3 * lda], xa, s3);
+            }
+            for (int off = 16; off > 0; off >>= 1) {
+                s0 += __shfl_xor_sync(0xffffffffu, s0, off);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, off);
+                s2 += __shfl_xor_sync(0xffffffffu, s2, off);
+                s3 += __shfl_xor_sync(0xffffffffu, s3, off);
+            }
+            if (lane == 0) {
+                double* o = scratch + c * kTile + col;
+                o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3;
+            }
         }
-        for (; r < r1; r += 32) {
-            const double xa = xs[r - r0];
-            s0 = fma(L0[r], xa, s0); s1 = fma(L0[r + lda], xa, s1);
-            s2 = fma(L0[r + 2 * lda], xa, s2); s3 = fma(L0[r + 3 * lda], xa, s3);
-        }
-        for (int off = 16; off > 0; off >>= 1) {
-            s0 += __shfl_xor_sync(0xffffffffu, s0, off);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, off);
-            s2 += __shfl_xor_sync(0xffffffffu, s2, off);
-            s3 += __shfl_xor_sync(0xffffffffu, s3, off);
-        }
-        if (lane == 0) {
-            double* o = scratch + c * kTile + col;
-            o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3;
-        }
+    } else if (t < kTile) {
+        scratch[c * kTile + t] = 0.0;
     }
-    __shared__ bool is_last;
-    __shared__ double tv[kTile];
     __threadfence();
     __syncthreads();
     if (t == 0) {
@@ -402,11 +485,16 @@ backsolve_step_kernel(const double* A_, long lda, long strideA, const double* Mi
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    if (t < kTile) {
+    {
+        // thread (h, col): h = t / 128 sums the partials of CTAs h, h + 2, ... (independent loads, fixed order)
+        const int col = t & (kTile - 1), h = t >> 7;
         double s = 0.0;
-        for (int cc = 0; cc < G; ++cc) s += __ldcg(&scratch[cc * kTile + t]);
-        tv[t] = sgn[t] * (v[kb * kTile + t] - s);
+#pragma unroll 8
+        for (int cc = h; cc < G; cc += 2) s += __ldcg(&scratch[cc * kTile + col]);
+        part[h][col] = s;
     }
+    __syncthreads();
+    if (t < kTile) tv[t] = sgn[t] * (v[kb * kTile + t] - (part[0][t] + part[1][t]));
     __syncthreads();
     for (int i = warp; i < kTile; i += 8) {
         // x_i = sum_{j >= i} M[j, i] (S t)[j]
@@ -493,19 +581,23 @@ __global__ void scf_init_kernel(ScfState* state, double damping, int batch) {
 
 cudaError_t launch_gemm_nt(const GemmArgs& g, int m_tiles, int n_tiles, int batch, cudaStream_t stream) {
     if (m_tiles <= 0 || n_tiles <= 0) return cudaSuccess;
+    GemmArgs args = g;
+    args.m_tiles = m_tiles;
+    args.n_tiles = n_tiles;
+    dim3 grid(m_tiles * n_tiles, 1, batch);
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    dim3 grid(m_tiles, n_tiles, batch);
-    gemm_nt_kernel<<<grid, kGemmThreads, kGemmSmem, stream>>>(g);
+    gemm_nt_kernel<<<grid, kGemmThreads, kGemmSmem, stream>>>(args);
     return cudaGetLastError();
 }
 
 cudaError_t launch_potrf_tile(double* A, long lda, long strideA, double* Linv, long strideLinv, double* sgn,
-                              long strideSgn, ScfState* state, double pivot_tol, int batch, cudaStream_t stream) {
+                              long strideSgn, int* neg_cnt, int* neg_idx, long strideNeg, ScfState* state,
+                              double pivot_tol, int batch, cudaStream_t stream) {
     static bool configured = false;
     if (!configured) {
         cudaError_t e =
@@ -515,7 +607,7 @@ cudaError_t launch_potrf_tile(double* A, long lda, long strideA, double* Linv, l
     }
     dim3 grid(1, 1, batch);
     potrf_tile_kernel<<<grid, kPotrfThreads, kPotrfSmem, stream>>>(A, lda, strideA, Linv, strideLinv, sgn, strideSgn,
-                                                                   state, pivot_tol);
+                                                                   neg_cnt, neg_idx, strideNeg, state, pivot_tol);
     return cudaGetLastError();
 }
 
@@ -553,11 +645,11 @@ cudaError_t launch_backsolve_step(const double* A, long lda, long strideA, const
                                   double* scratch, long scratch_stride, unsigned* counters, const ScfState* state,
                                   int batch, cudaStream_t stream) {
     const int rows = NP - (kb + 1) * kTile;
-    int G = (rows + kBackRows - 1) / kBackRows;
+    int G = (rows + kTile - 1) / kTile;          // 128-row slabs: latency-bound, so favour many CTAs
     if (G < 1) G = 1;
+    if (batch > 1 && G > 8) G = 8;               // batched frames already fill the machine
     if (G > kBackMaxCtas) G = kBackMaxCtas;
-    // the x slab staged in shared memory holds at most 4 * kBackRows rows per CTA
-    while ((((rows + G - 1) / G + 63) & ~63) > 4 * kBackRows) ++G;
+    while ((((rows + G - 1) / G + 63) & ~63) > kBackSlab) ++G;
     dim3 grid(G, 1, batch);
     backsolve_step_kernel<<<grid, 256, 0, stream>>>(A, lda, strideA, Linv, strideLinv, sgn, strideSgn, NP, kb, v,
                                                     v_stride, scratch, scratch_stride, counters, state);

@@ -163,6 +163,10 @@ int32_t cheq_dbg_cholesky_solve(cheq_ctx* ctx, uint64_t n, const double* a, uint
                                 double* x_out, double* l_out /* nullable, n x n */);
 int32_t cheq_dbg_gemm_nt(cheq_ctx* ctx, uint64_t m, uint64_t n, uint64_t k, const double* a,
                          const double* b, double* c, int32_t subtract);
+/* Times `reps` launches of the same GEMM on device-resident operands (CUDA events); ms_out = ms per launch.
+ * lower != 0 skips the tiles above the diagonal (the symmetric trailing update). */
+int32_t cheq_dbg_gemm_bench(cheq_ctx* ctx, uint64_t m, uint64_t n, uint64_t k, int32_t lower, int32_t subtract,
+                            int32_t reps, double* ms_out);
 
 /* Host-only: evaluates the STO pair table (built exactly as for the device) in fp64 on the CPU.  Used to
  * test the table construction without a GPU; not a solve path.  Distance in bohr, result in Hartree. */
