@@ -28,7 +28,7 @@ class Stats(C.Structure):
                 ("n_hydrogen", C.c_uint64), ("n_padded", C.c_uint64), ("iterations", C.c_uint32),
                 ("pair_types", C.c_uint32), ("flops_factor", C.c_double), ("bytes_assemble", C.c_double),
                 ("lu_fallback_frames", C.c_uint64), ("gemm_ms", C.c_double), ("gemm_flops", C.c_double),
-                ("gemm_launches", C.c_uint64)]
+                ("gemm_launches", C.c_uint64), ("potrf_ms", C.c_double), ("backsolve_ms", C.c_double)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -54,6 +54,7 @@ SIGNATURES = {
     "cheq_external_potential": (_I32, [_P, _U64, _P, _P, _P, C.POINTER(External), _D, _U8, _P]),
     "cheq_dbg_cholesky_solve": (_I32, [_P, _U64, _P, _U64, _P, _P, _P]),
     "cheq_dbg_gemm_nt": (_I32, [_P, _U64, _U64, _U64, _P, _P, _P, _I32]),
+    "cheq_dbg_dfma_rate": (_I32, [_P, C.POINTER(_D)]),
     "cheq_dbg_gemm_bench": (_I32, [_P, _U64, _U64, _U64, _I32, _I32, _I32, C.POINTER(_D)]),
     "cheq_host_sto_table_eval": (_D, [_I32, _D, _I32, _D, _D, C.POINTER(_I32), C.POINTER(_I32), C.POINTER(_I32),
                                       C.POINTER(_D)]),

@@ -102,7 +102,7 @@ struct cheq_ctx {
     // device workspace (grow-only)
     DeviceBuffer in_xyz, in_chi, in_hard, in_radius, in_nq, perm, type, x, y, z, diag, chi, hard, vext, A, S0,
         Linv, v, q, scratch, counters, state, active, blob, pc_xyz, pc_q, pc_type, out_q, misc0, misc1, misc2,
-        lu_f, lu_piv, sgn, sgn_flags;
+        lu_f, lu_piv, sgn, sgn_flags, xsol;
     ScfState* h_state = nullptr;   // pinned
     int* h_active = nullptr;       // pinned
     size_t h_state_cap = 0;
@@ -111,6 +111,7 @@ struct cheq_ctx {
     // optional per-launch timing of the dominant kernel (gemm_nt_kernel) with CUDA events on the stream
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;   // pairs (start, stop)
+    std::vector<int> prof_cat;              // category of each pair: 0 GEMM, 1 diagonal-tile factorisation, 2 back substitution
     size_t prof_used = 0;
     double prof_flops = 0.0;
 };
@@ -351,22 +352,31 @@ struct Dense {
 // Matrix entries are O(1..30) eV, so accepted pivots bound the element growth by ~1e5 (error ~1e-11).
 constexpr double kPivotTol = 1.0e-4;
 
-int launch_gemm_timed(cheq_ctx* ctx, const GemmArgs& g, int mt, int nt, int batch, double flops) {
-    if (!ctx->profile) {
-        LAUNCH(launch_gemm_nt(g, mt, nt, batch, ctx->stream));
-        return CHEQ_OK;
-    }
+int prof_begin(cheq_ctx* ctx, int category) {
+    if (!ctx->profile) return CHEQ_OK;
     if (ctx->prof_used + 2 > ctx->prof_events.size()) {
         const size_t old = ctx->prof_events.size();
         ctx->prof_events.resize(old + 4096, nullptr);
         for (size_t i = old; i < ctx->prof_events.size(); ++i) CU(cudaEventCreate(&ctx->prof_events[i]));
     }
+    if (ctx->prof_cat.size() < ctx->prof_events.size() / 2) ctx->prof_cat.resize(ctx->prof_events.size() / 2);
+    ctx->prof_cat[ctx->prof_used / 2] = category;
     CU(cudaEventRecord(ctx->prof_events[ctx->prof_used], ctx->stream));
-    LAUNCH(launch_gemm_nt(g, mt, nt, batch, ctx->stream));
+    return CHEQ_OK;
+}
+int prof_end(cheq_ctx* ctx) {
+    if (!ctx->profile) return CHEQ_OK;
     CU(cudaEventRecord(ctx->prof_events[ctx->prof_used + 1], ctx->stream));
     ctx->prof_used += 2;
-    ctx->prof_flops += flops * batch;
     return CHEQ_OK;
+}
+
+int launch_gemm_timed(cheq_ctx* ctx, const GemmArgs& g, int mt, int nt, int batch, double flops) {
+    int rc = prof_begin(ctx, 0);
+    if (rc) return rc;
+    LAUNCH(launch_gemm_nt(g, mt, nt, batch, ctx->stream));
+    if (ctx->profile) ctx->prof_flops += flops * batch;
+    return prof_end(ctx);
 }
 
 // Recursive tall-panel Cholesky of columns [j0, j0 + n) with all rows down to MT (the rows below the panel are
@@ -377,8 +387,10 @@ int factor_panel(Dense& D, int j0, int n) {
     if (n == kTile) {
         double* Ajj = D.A + (long)j0 + (long)j0 * D.ld;
         double* Lk = D.Linv + (long)(j0 / kTile) * kTile * kTile;
+        if (int rcp = prof_begin(ctx, 1)) return rcp;
         LAUNCH(launch_potrf_tile(Ajj, D.ld, D.strideA, Lk, D.strideLinv, D.sgn + j0, D.strideSgn, D.neg_cnt + j0 / kTile,
                                  D.neg_idx + (long)j0, D.strideNeg, D.state, kPivotTol, D.batch, ctx->stream));
+        if (int rcp = prof_end(ctx)) return rcp;
         const int mt = (D.MT - j0 - kTile) / kTile;
         if (mt > 0) {
             GemmArgs g{};
@@ -463,13 +475,14 @@ int schur_update(Dense& D, int k, int ncols) {
     return CHEQ_OK;
 }
 
-int backsolve(Dense& D, int NP, double* v, long v_stride) {
+// x = L^-T v.  v is consumed (its blocks become the updated right-hand sides), the solution goes to x.
+int backsolve(Dense& D, int NP, double* v, double* x, long v_stride) {
     cheq_ctx* ctx = D.ctx;
+    if (int rcp = prof_begin(ctx, 2)) return rcp;
     for (int kb = NP / kTile - 1; kb >= 0; --kb)
-        LAUNCH(launch_backsolve_step(D.A, D.ld, D.strideA, D.Linv, D.strideLinv, D.sgn, D.strideSgn, NP, kb, v, v_stride,
-                                     ctx->scratch.as<double>(), (long)backsolve_max_ctas() * kTile,
-                                     ctx->counters.as<unsigned>(), D.state, D.batch, ctx->stream));
-    return CHEQ_OK;
+        LAUNCH(launch_backsolve_step(D.A, D.ld, D.strideA, D.Linv, D.strideLinv, D.sgn, D.strideSgn, NP, kb, v, x,
+                                     v_stride, D.state, D.batch, ctx->stream));
+    return prof_end(ctx);
 }
 
 int ensure_host_state(cheq_ctx* ctx, size_t batch) {
@@ -600,6 +613,7 @@ int prepare_and_assemble(cheq_ctx* ctx, const SolveIO& io, long frame0, int batc
     CU(ctx->y.ensure(vec));
     CU(ctx->z.ensure(vec));
     CU(ctx->v.ensure(vec));
+    CU(ctx->xsol.ensure(vec));
     CU(ctx->q.ensure(vec));
     CU(ctx->diag.ensure(L.NP * 8));
     CU(ctx->chi.ensure(L.NP * 8));
@@ -719,6 +733,7 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
     if (L.scf && o.damping_kind != CHEQ_DAMPING_NONE) damping0 = o.damping_value;
     LAUNCH(launch_scf_init(ctx->state.as<ScfState>(), damping0, batch, st));
     double* v = ctx->v.as<double>();
+    double* xs = ctx->xsol.as<double>();
     double* q = ctx->q.as<double>();
     int rc;
 
@@ -728,9 +743,9 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
         if (rc) return rc;
         CU(cudaEventRecord(ctx->ev[3], st));
         LAUNCH(launch_mu(D.A, D.ld, D.strideA, L.NP, io.total_charge, v, L.NP, D.sgn, D.strideSgn, D.state, batch, st));
-        rc = backsolve(D, L.NP, v, L.NP);
+        rc = backsolve(D, L.NP, v, xs, L.NP);
         if (rc) return rc;
-        LAUNCH(launch_scf_mix(v, q, L.NP, ctx->type.as<uint8_t>(), L.NP, D.state, batch, st));
+        LAUNCH(launch_scf_mix(xs, q, L.NP, ctx->type.as<uint8_t>(), L.NP, D.state, batch, st));
         CU(cudaMemsetAsync(ctx->active.p, 0, sizeof(int), st));
         LAUNCH(launch_scf_decide(D.state, INFINITY, CHEQ_DAMPING_NONE, batch, ctx->active.as<int>(), st));
         CU(cudaMemcpyAsync(ctx->h_state, ctx->state.p, sizeof(ScfState) * batch, cudaMemcpyDeviceToHost, st));
@@ -770,9 +785,9 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
         rc = factor_panel(D, L.nxp, L.nhp);
         if (rc) return rc;
         LAUNCH(launch_mu(D.A, D.ld, D.strideA, L.NP, io.total_charge, v, L.NP, D.sgn, D.strideSgn, D.state, batch, st));
-        rc = backsolve(D, L.NP, v, L.NP);
+        rc = backsolve(D, L.NP, v, xs, L.NP);
         if (rc) return rc;
-        LAUNCH(launch_scf_mix(v, q, L.NP, ctx->type.as<uint8_t>(), L.NP, D.state, batch, st));
+        LAUNCH(launch_scf_mix(xs, q, L.NP, ctx->type.as<uint8_t>(), L.NP, D.state, batch, st));
         CU(cudaMemsetAsync(ctx->active.p, 0, sizeof(int), st));
         LAUNCH(launch_scf_decide(D.state, o.tolerance, o.damping_kind, batch, ctx->active.as<int>(), st));
         CU(cudaMemcpyAsync(ctx->h_active, ctx->active.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -956,15 +971,20 @@ int solve_impl(cheq_ctx* ctx, const SolveIO& io) {
     }
     ctx->stats.kernel_launches = ctx->launches;
     if (ctx->profile) {
-        double ms_sum = 0.0;
+        double ms_sum[3] = {0.0, 0.0, 0.0};
+        uint64_t n_gemm = 0;
         for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
             float ms = 0;
             cudaEventElapsedTime(&ms, ctx->prof_events[i], ctx->prof_events[i + 1]);
-            ms_sum += ms;
+            const int cat = ctx->prof_cat[i / 2];
+            ms_sum[cat] += ms;
+            n_gemm += (cat == 0);
         }
-        ctx->stats.gemm_ms = ms_sum;
-        ctx->stats.gemm_launches = ctx->prof_used / 2;
+        ctx->stats.gemm_ms = ms_sum[0];
+        ctx->stats.gemm_launches = n_gemm;
         ctx->stats.gemm_flops = ctx->prof_flops;
+        ctx->stats.potrf_ms = ms_sum[1];
+        ctx->stats.backsolve_ms = ms_sum[2];
     }
     ctx->stats.ms_total = ms_since(t_total);
     if (io.frames > 1 && io.status_out) return CHEQ_OK;
@@ -1009,7 +1029,7 @@ void cheq_ctx_destroy(cheq_ctx* ctx) {
                             &ctx->type, &ctx->x, &ctx->y, &ctx->z, &ctx->diag, &ctx->chi, &ctx->hard, &ctx->vext,
                             &ctx->A, &ctx->S0, &ctx->Linv, &ctx->v, &ctx->q, &ctx->scratch, &ctx->counters,
                             &ctx->state, &ctx->active, &ctx->blob, &ctx->pc_xyz, &ctx->pc_q, &ctx->pc_type,
-                            &ctx->out_q, &ctx->misc0, &ctx->misc1, &ctx->misc2, &ctx->lu_f, &ctx->lu_piv, &ctx->sgn, &ctx->sgn_flags};
+                            &ctx->out_q, &ctx->misc0, &ctx->misc1, &ctx->misc2, &ctx->lu_f, &ctx->lu_piv, &ctx->sgn, &ctx->sgn_flags, &ctx->xsol};
     for (DeviceBuffer* b : bufs) b->release();
     if (ctx->h_state) cudaFreeHost(ctx->h_state);
     if (ctx->h_active) cudaFreeHost(ctx->h_active);
@@ -1298,6 +1318,7 @@ int32_t cheq_dbg_cholesky_solve(cheq_ctx* ctx, uint64_t n_, const double* a, uin
     CU(ctx->A.ensure(h.size() * 8));
     CU(ctx->Linv.ensure((size_t)NP * kTile * 8));
     CU(ctx->v.ensure(NP * 8));
+    CU(ctx->xsol.ensure(NP * 8));
     CU(ctx->scratch.ensure((size_t)backsolve_max_ctas() * kTile * 8));
     CU(ctx->counters.ensure(sizeof(unsigned)));
     CU(ctx->state.ensure(sizeof(ScfState)));
@@ -1317,9 +1338,9 @@ int32_t cheq_dbg_cholesky_solve(cheq_ctx* ctx, uint64_t n_, const double* a, uin
     for (uint64_t r = 0; r < nrhs; ++r) {
         // v = forward-substituted rhs r (row NP + r)
         CU(cudaMemcpy2DAsync(ctx->v.p, 8, ctx->A.as<double>() + NP + r, ld * 8, 8, NP, cudaMemcpyDeviceToDevice, st));
-        rc = backsolve(D, NP, ctx->v.as<double>(), NP);
+        rc = backsolve(D, NP, ctx->v.as<double>(), ctx->xsol.as<double>(), NP);
         if (rc) return rc;
-        CU(cudaMemcpyAsync(xv.data(), ctx->v.p, NP * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(xv.data(), ctx->xsol.p, NP * 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         for (long i = 0; i < n; ++i) x_out[i + r * n] = xv[i];
     }
@@ -1361,6 +1382,7 @@ int32_t cheq_dbg_gemm_bench(cheq_ctx* ctx, uint64_t m, uint64_t n, uint64_t k, i
     g.K = (int)k;
     g.lower = lower & 1;
     g.subtract = subtract ? 1 : 0;
+    if (lower & 0x30) set_gemm_warps((lower & 0x10) ? 8 : 16);   // debug: bit 4 -> 8 warps, bit 5 -> 16 warps
     LAUNCH(launch_gemm_nt(g, (int)(m / kTile), (int)(n / kTile), 1, st));   // warm-up
     CU(cudaEventRecord(ctx->ev[0], st));
     for (int r = 0; r < reps; ++r) LAUNCH(launch_gemm_nt(g, (int)(m / kTile), (int)(n / kTile), 1, st));
@@ -1369,6 +1391,38 @@ int32_t cheq_dbg_gemm_bench(cheq_ctx* ctx, uint64_t m, uint64_t n, uint64_t k, i
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
     *ms_out = ms / reps;
+    return CHEQ_OK;
+}
+
+int32_t cheq_dbg_dfma_rate(cheq_ctx* ctx, double* tflops_out) {
+    if (!ctx || !tflops_out) return CHEQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->err.clear();
+    CU(cudaSetDevice(ctx->device));
+    const int blocks = 148 * 8, iters = 1 << 15;
+    CU(ctx->misc0.ensure((size_t)blocks * 256 * 8));
+    LAUNCH(launch_dfma_rate(ctx->misc0.as<double>(), blocks, 1024, ctx->stream));
+    CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+    LAUNCH(launch_dfma_rate(ctx->misc0.as<double>(), blocks, iters, ctx->stream));
+    CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    *tflops_out = 2.0 * 8.0 * iters * (double)blocks * 256.0 / (ms * 1e-3) / 1e12;
+    // DMMA issue rate at 2, 4 and 8 warps per SM sub-partition, reported through the error string (debug aid)
+    std::string report;
+    for (int threads : {128, 256, 512}) {
+        const int b2 = 148, it2 = 1 << 14;
+        LAUNCH(launch_dmma_rate(ctx->misc0.as<double>(), b2, threads, 256, ctx->stream));
+        CU(cudaEventRecord(ctx->ev[0], ctx->stream));
+        LAUNCH(launch_dmma_rate(ctx->misc0.as<double>(), b2, threads, it2, ctx->stream));
+        CU(cudaEventRecord(ctx->ev[1], ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+        const double tf = 512.0 * 16.0 * it2 * (double)b2 * (threads / 32) / (ms * 1e-3) / 1e12;
+        report += "dmma " + std::to_string(threads / 128) + " warps/SMSP: " + std::to_string(tf) + " TF/s; ";
+    }
+    ctx->err = report;
     return CHEQ_OK;
 }
 

@@ -74,6 +74,9 @@ cudaError_t launch_export_matrix(int NP, long ld, const double* A, const int* pe
 
 // ---- dense (kernels_dense.cu) ------------------------------------------------------------------------------
 cudaError_t launch_gemm_nt(const GemmArgs& g, int m_tiles, int n_tiles, int batch, cudaStream_t stream);
+cudaError_t launch_dmma_rate(double* out, int blocks, int threads, int iters, cudaStream_t stream);
+cudaError_t launch_dfma_rate(double* out, int blocks, int iters, cudaStream_t stream);
+void set_gemm_warps(int warps);   // tuning knob: 8 or 16 warps per GEMM CTA
 // A = L S L^T of one 128 x 128 diagonal block in place (lower) + M = S L^-1 (dense 128 x 128, ld 128) + the signs.
 // |pivot| <= pivot_tol sets state.info (the caller then falls back to the pivoted LU).
 cudaError_t launch_potrf_tile(double* A, long lda, long strideA, double* Linv, long strideLinv, double* sgn,
@@ -91,11 +94,11 @@ cudaError_t launch_set_h_diagonal(double* A, long lda, long strideA, const doubl
 cudaError_t launch_mu(const double* A, long lda, long strideA, int NP, double total_charge, double* v,
                       long v_stride, const double* sgn, long strideSgn, ScfState* state, int batch,
                       cudaStream_t stream);
-// one block-row step (block kb) of the backward substitution L^T x = v, in place in v
+// one block-row step (block kb) of the backward substitution L^T x = v (right-looking): x_kb is written to x,
+// the right-hand sides of the earlier blocks are updated in v
 cudaError_t launch_backsolve_step(const double* A, long lda, long strideA, const double* Linv, long strideLinv,
-                                  const double* sgn, long strideSgn, int NP, int kb, double* v, long v_stride,
-                                  double* scratch, long scratch_stride, unsigned* counters, const ScfState* state,
-                                  int batch, cudaStream_t stream);
+                                  const double* sgn, long strideSgn, int NP, int kb, double* v, double* x,
+                                  long v_stride, const ScfState* state, int batch, cudaStream_t stream);
 int backsolve_max_ctas();
 // delta = max |x - q| over real atoms; q <- (1 - d) q + d x
 cudaError_t launch_scf_mix(const double* x, double* q, long stride, const uint8_t* type, int NP, ScfState* state,

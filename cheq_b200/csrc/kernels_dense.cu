@@ -56,7 +56,11 @@ constexpr int kGroupM = 8;   // tile rows per rasterisation group: their A slabs
 // scaling B fragments in the loop costs 4 % of DMMA throughput, a flagged branch 11 %); negative pivots are rare
 // (one per negative eigenvalue), so the epilogue applies  A S B^T = A B^T - 2 sum_{k: s_k = -1} a_k b_k^T  as
 // rank-1 corrections to the accumulators, driven by the per-tile lists the factorisation leaf writes.
-__global__ void __launch_bounds__(kGemmThreads, 1) gemm_nt_kernel(GemmArgs g) {
+template <int FM>
+__global__ void __launch_bounds__((128 / (16 * FM)) * 4 * 32, 1) gemm_nt_kernel(GemmArgs g) {
+    constexpr int kWarpsM = 128 / (16 * FM);          // 2 or 4
+    constexpr int kThreads = kWarpsM * 4 * 32;        // 256 or 512
+    constexpr int kChunks = 1024 / kThreads;          // 16-byte chunks per thread per operand per stage
     // grouped rasterisation: consecutive CTAs walk the tile columns of a group of kGroupM tile rows
     const int frame = blockIdx.z;
     int tile_m, tile_n;
@@ -80,7 +84,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_nt_kernel(GemmArgs g) {
     double* C = g.C + (long)frame * g.strideC + (long)tile_m * BM + (long)tile_n * BN * g.ldc;
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int wm = warp & 1, wn = warp >> 1;   // 2 x 4 warps, warp tile 64 x 32
+    const int wm = warp % kWarpsM, wn = warp / kWarpsM;   // kWarpsM x 4 warps, warp tile (16 FM) x 32
     const int gq = lane >> 2, q = lane & 3;
 
     auto load_stage = [&](int stage, int ktile) {
@@ -88,17 +92,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_nt_kernel(GemmArgs g) {
         double* bs = Bs + stage * BK * LDT;
         const long k0 = (long)ktile * BK;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int c = t + i * kGemmThreads;   // 0..1023
+        for (int i = 0; i < kChunks; ++i) {
+            const int c = t + i * kThreads;   // 0..1023
             const int kr = c >> 6, mc = c & 63;
             cp_async16(as + kr * LDT + 2 * mc, A + 2 * mc + (k0 + kr) * g.lda);
             cp_async16(bs + kr * LDT + 2 * mc, B + 2 * mc + (k0 + kr) * g.ldb);
         }
     };
 
-    double acc[4][2][2][2][2];  // [fm][row parity][fn][col parity][e]
+    double acc[FM][2][2][2][2];  // [fm][row parity][fn][col parity][e]
 #pragma unroll
-    for (int i = 0; i < 64; ++i) ((double*)acc)[i] = 0.0;
+    for (int i = 0; i < FM * 16; ++i) ((double*)acc)[i] = 0.0;
 
     const int kt = g.K / BK;
 #pragma unroll
@@ -116,17 +120,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_nt_kernel(GemmArgs g) {
             cp_async_commit();
         }
         const int stage = it % STAGES;
-        const double* as = As + stage * BK * LDT + wm * 64 + 2 * gq;
+        const double* as = As + stage * BK * LDT + wm * (16 * FM) + 2 * gq;
         const double* bs = Bs + stage * BK * LDT + wn * 32 + 2 * gq;
 #pragma unroll
         for (int kk = 0; kk < BK / 4; ++kk) {
-            double2 a[4], b[2];
+            double2 a[FM], b[2];
 #pragma unroll
-            for (int fm = 0; fm < 4; ++fm) a[fm] = *(const double2*)(as + (kk * 4 + q) * LDT + fm * 16);
+            for (int fm = 0; fm < FM; ++fm) a[fm] = *(const double2*)(as + (kk * 4 + q) * LDT + fm * 16);
 #pragma unroll
             for (int fn = 0; fn < 2; ++fn) b[fn] = *(const double2*)(bs + (kk * 4 + q) * LDT + fn * 16);
 #pragma unroll
-            for (int fm = 0; fm < 4; ++fm)
+            for (int fm = 0; fm < FM; ++fm)
 #pragma unroll
                 for (int fn = 0; fn < 2; ++fn) {
                     dmma884(acc[fm][0][fn][0][0], acc[fm][0][fn][0][1], a[fm].x, b[fn].x);
@@ -146,19 +150,19 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_nt_kernel(GemmArgs g) {
             const int nneg = cnt[kt128];
             for (int j = 0; j < nneg; ++j) {
                 const long k = (long)kt128 * kTile + idx[kt128 * kTile + j];
-                const double* ak = A + k * g.lda + wm * 64 + 2 * gq;
+                const double* ak = A + k * g.lda + wm * (16 * FM) + 2 * gq;
                 const double* bk = B + k * g.ldb + wn * 32 + 4 * q;
-                double2 av[4];
+                double2 av[FM];
                 double bv[2][2][2];   // [fn][pc][e]: column 4 q + 2 e + pc of the 16-column group
 #pragma unroll
-                for (int fm = 0; fm < 4; ++fm) av[fm] = *(const double2*)(ak + fm * 16);
+                for (int fm = 0; fm < FM; ++fm) av[fm] = *(const double2*)(ak + fm * 16);
 #pragma unroll
                 for (int fn = 0; fn < 2; ++fn) {
                     const double2 lo = *(const double2*)(bk + fn * 16), hi = *(const double2*)(bk + fn * 16 + 2);
                     bv[fn][0][0] = lo.x; bv[fn][1][0] = lo.y; bv[fn][0][1] = hi.x; bv[fn][1][1] = hi.y;
                 }
 #pragma unroll
-                for (int fm = 0; fm < 4; ++fm)
+                for (int fm = 0; fm < FM; ++fm)
 #pragma unroll
                     for (int fn = 0; fn < 2; ++fn)
 #pragma unroll
@@ -175,8 +179,8 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_nt_kernel(GemmArgs g) {
     // epilogue: thread owns rows (2 gq, 2 gq + 1) of each 16-row group and columns 4 q + 2 e + pc of each
     // 16-column group
 #pragma unroll
-    for (int fm = 0; fm < 4; ++fm) {
-        const int row = wm * 64 + fm * 16 + 2 * gq;
+    for (int fm = 0; fm < FM; ++fm) {
+        const int row = wm * (16 * FM) + fm * 16 + 2 * gq;
 #pragma unroll
         for (int fn = 0; fn < 2; ++fn)
 #pragma unroll
@@ -412,99 +416,64 @@ mu_kernel(const double* A_, long lda, long strideA, int NP, double total_charge,
     for (int j = threadIdx.x; j < NP; j += 1024) v[j] = fc[(long)j * lda] - mu * f1[(long)j * lda];
 }
 
-// Backward substitution L^T x = v, block row kb:  x_kb = L_kk^-T (v_kb - L[rows below, kb cols]^T x[rows below]),
-// with L_kk^-T t = M_kk^T (S t).  Each CTA reduces a slab of rows of the 128-column panel (each warp keeps
-// 4 columns x 2 row groups of loads in flight) and writes 128 partial sums; the last CTA to finish adds the
-// partials in a fixed order (deterministic) and applies the diagonal block.
-constexpr int kBackMaxCtas = 296;
-constexpr int kBackSlab = 1024;   // rows of x staged in shared memory per CTA (upper bound on the slab)
+// Backward substitution L^T x = v, right-looking, block row kb (from the last to the first):
+//   x_kb = L_kk^-T v_kb = M_kk^T (S v_kb);   v_j -= L[kb rows, j]^T x_kb  for every column j < 128 kb.
+// Every CTA recomputes x_kb (128 x 128 triangular product, M from L2) and then owns 64 columns of the update, one
+// warp per column group: no cross-CTA reduction, fixed summation order.  CTA 0 also stores x_kb.
+constexpr int kBackCols = 64;
 __global__ void __launch_bounds__(256)
 backsolve_step_kernel(const double* A_, long lda, long strideA, const double* Minv_, long strideM,
-                      const double* sgn_, long strideSgn, int NP, int kb, double* v_, long v_stride,
-                      double* scratch_, long scratch_stride, unsigned* counters, const ScfState* state) {
+                      const double* sgn_, long strideSgn, int kb, double* v_, double* x_, long v_stride,
+                      const ScfState* state) {
     const int frame = blockIdx.z;
     if (state && !state[frame].active) return;
     const double* A = A_ + (long)frame * strideA;
     const double* Minv = Minv_ + (long)frame * strideM + (long)kb * kTile * kTile;
     const double* sgn = sgn_ + (long)frame * strideSgn + kb * kTile;
     double* v = v_ + (long)frame * v_stride;
-    double* scratch = scratch_ + (long)frame * scratch_stride;
-    const int G = gridDim.x, c = blockIdx.x;
+    double* x = x_ + (long)frame * v_stride;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int r_lo = (kb + 1) * kTile;
-    const int rows = NP - r_lo;
-    int chunk = (rows + G - 1) / G;
-    chunk = (chunk + 63) & ~63;
-    const int r0 = r_lo + c * chunk;
-    const int r1 = min(NP, r0 + chunk);
-    __shared__ double xs[kBackSlab];
     __shared__ double tv[kTile];
-    __shared__ double part[2][kTile];
-    __shared__ bool is_last;
-    for (int r = r0 + t; r < r1; r += 256) xs[r - r0] = v[r];
-    __syncthreads();
-
-    if (r0 < r1) {
-        for (int cg = 0; cg < 4; ++cg) {
-            const int col = warp * 16 + cg * 4;
-            const double* L0 = A + (long)(kb * kTile + col) * lda;
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            int r = r0 + lane;
-            for (; r + 32 < r1; r += 64) {
-                const double xa = xs[r - r0], xb = xs[r + 32 - r0];
-                const double a0 = L0[r], a1 = L0[r + lda], a2 = L0[r + 2 * lda], a3 = L0[r + 3 * lda];
-                const double b0 = L0[r + 32], b1 = L0[r + 32 + lda], b2 = L0[r + 32 + 2 * lda], b3 = L0[r + 32 + 3 * lda];
-                s0 = fma(a0, xa, s0); s1 = fma(a1, xa, s1); s2 = fma(a2, xa, s2); s3 = fma(a3, xa, s3);
-                s0 = fma(b0, xb, s0); s1 = fma(b1, xb, s1); s2 = fma(b2, xb, s2); s3 = fma(b3, xb, s3);
-            }
-            for (; r < r1; r += 32) {
-                const double xa = xs[r - r0];
-                s0 = fma(L0[r], xa, s0); s1 = fma(L0[r + lda], xa, s1);
-                s2 = fma(L0[r + 2 * lda], xa, s2); s3 = fma(L0[r + 3 * lda], xa, s3);
-            }
-            for (int off = 16; off > 0; off >>= 1) {
-                s0 += __shfl_xor_sync(0xffffffffu, s0, off);
-                s1 += __shfl_xor_sync(0xffffffffu, s1, off);
-                s2 += __shfl_xor_sync(0xffffffffu, s2, off);
-                s3 += __shfl_xor_sync(0xffffffffu, s3, off);
-            }
-            if (lane == 0) {
-                double* o = scratch + c * kTile + col;
-                o[0] = s0; o[1] = s1; o[2] = s2; o[3] = s3;
-            }
-        }
-    } else if (t < kTile) {
-        scratch[c * kTile + t] = 0.0;
-    }
-    __threadfence();
-    __syncthreads();
-    if (t == 0) {
-        const unsigned prev = atomicAdd(&counters[frame], 1u);
-        is_last = (prev == (unsigned)(G - 1));
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    {
-        // thread (h, col): h = t / 128 sums the partials of CTAs h, h + 2, ... (independent loads, fixed order)
-        const int col = t & (kTile - 1), h = t >> 7;
-        double s = 0.0;
-#pragma unroll 8
-        for (int cc = h; cc < G; cc += 2) s += __ldcg(&scratch[cc * kTile + col]);
-        part[h][col] = s;
-    }
-    __syncthreads();
-    if (t < kTile) tv[t] = sgn[t] * (v[kb * kTile + t] - (part[0][t] + part[1][t]));
+    __shared__ double xs[kTile];
+    if (t < kTile) tv[t] = sgn[t] * v[kb * kTile + t];
     __syncthreads();
     for (int i = warp; i < kTile; i += 8) {
-        // x_i = sum_{j >= i} M[j, i] (S t)[j]
+        // x_i = sum_{j >= i} M[j, i] (S v)[j]
         const double* Xc = Minv + (long)i * kTile;
         double s = 0.0;
-        for (int j = i + lane; j < kTile; j += 32) s = fma(Xc[j], tv[j], s);
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const int j = lane + 32 * jj;
+            if (j >= i) s = fma(Xc[j], tv[j], s);
+        }
         for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-        if (lane == 0) v[kb * kTile + i] = s;
+        if (lane == 0) xs[i] = s;
     }
-    if (t == 0) counters[frame] = 0u;
+    __syncthreads();
+    if (blockIdx.x == 0 && t < kTile) x[kb * kTile + t] = xs[t];
+    // update of the earlier blocks: this CTA's columns [c0, c0 + 64)
+    const int c0 = blockIdx.x * kBackCols;
+    if (c0 >= kb * kTile) return;
+    const double x0 = xs[lane], x1 = xs[lane + 32], x2 = xs[lane + 64], x3 = xs[lane + 96];
+    const double* Lr = A + (long)kb * kTile + lane;   // rows of block kb
+#pragma unroll
+    for (int cc = 0; cc < kBackCols / 8; cc += 2) {
+        const int ja = c0 + warp * (kBackCols / 8) + cc, jb = ja + 1;
+        const double* La = Lr + (long)ja * lda;
+        const double* Lb = Lr + (long)jb * lda;
+        double sa = La[0] * x0, sb = Lb[0] * x0;
+        sa = fma(La[32], x1, sa); sb = fma(Lb[32], x1, sb);
+        sa = fma(La[64], x2, sa); sb = fma(Lb[64], x2, sb);
+        sa = fma(La[96], x3, sa); sb = fma(Lb[96], x3, sb);
+        for (int off = 16; off > 0; off >>= 1) {
+            sa += __shfl_xor_sync(0xffffffffu, sa, off);
+            sb += __shfl_xor_sync(0xffffffffu, sb, off);
+        }
+        if (lane == 0) {
+            v[ja] -= sa;
+            v[jb] -= sb;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(256)
@@ -579,6 +548,46 @@ __global__ void scf_init_kernel(ScfState* state, double damping, int batch) {
 
 }  // namespace
 
+// FP64 FMA throughput probe (plain DFMA pipe, not the tensor path): 8 independent chains per thread.
+__global__ void __launch_bounds__(256) dfma_rate_kernel(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double x = 1.0000001, y = 1e-9;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, x, y); a1 = fma(a1, x, y); a2 = fma(a2, x, y); a3 = fma(a3, x, y);
+        a4 = fma(a4, x, y); a5 = fma(a5, x, y); a6 = fma(a6, x, y); a7 = fma(a7, x, y);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// DMMA.8x8x4 issue-rate probe: 32 independent accumulator pairs per warp, operands in registers.
+__global__ void dmma_rate_kernel(double* out, int iters) {
+    double acc[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i][0] = acc[i][1] = threadIdx.x * 1e-9 + i;
+    double a = 1.0000001 + threadIdx.x * 1e-12, b = 0.5 + threadIdx.x * 1e-12;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dmma884(acc[i][0], acc[i][1], a, b);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i][0] + acc[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+cudaError_t launch_dmma_rate(double* out, int blocks, int threads, int iters, cudaStream_t stream) {
+    dmma_rate_kernel<<<blocks, threads, 0, stream>>>(out, iters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dfma_rate(double* out, int blocks, int iters, cudaStream_t stream) {
+    dfma_rate_kernel<<<blocks, 256, 0, stream>>>(out, iters);
+    return cudaGetLastError();
+}
+
+int g_gemm_warps = 16;   // warps per GEMM CTA: 8 (64 x 32 warp tiles) or 16 (32 x 32)
+void set_gemm_warps(int w) { g_gemm_warps = (w == 8) ? 8 : 16; }
+
 cudaError_t launch_gemm_nt(const GemmArgs& g, int m_tiles, int n_tiles, int batch, cudaStream_t stream) {
     if (m_tiles <= 0 || n_tiles <= 0) return cudaSuccess;
     GemmArgs args = g;
@@ -587,11 +596,14 @@ cudaError_t launch_gemm_nt(const GemmArgs& g, int m_tiles, int n_tiles, int batc
     dim3 grid(m_tiles * n_tiles, 1, batch);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_nt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_nt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(gemm_nt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    gemm_nt_kernel<<<grid, kGemmThreads, kGemmSmem, stream>>>(args);
+    if (g_gemm_warps == 8) gemm_nt_kernel<4><<<grid, 256, kGemmSmem, stream>>>(args);
+    else gemm_nt_kernel<2><<<grid, 512, kGemmSmem, stream>>>(args);
     return cudaGetLastError();
 }
 
@@ -638,21 +650,17 @@ cudaError_t launch_mu(const double* A, long lda, long strideA, int NP, double to
     return cudaGetLastError();
 }
 
-int backsolve_max_ctas() { return kBackMaxCtas; }
+int backsolve_max_ctas() { return 1; }
 
 cudaError_t launch_backsolve_step(const double* A, long lda, long strideA, const double* Linv, long strideLinv,
-                                  const double* sgn, long strideSgn, int NP, int kb, double* v, long v_stride,
-                                  double* scratch, long scratch_stride, unsigned* counters, const ScfState* state,
-                                  int batch, cudaStream_t stream) {
-    const int rows = NP - (kb + 1) * kTile;
-    int G = (rows + kTile - 1) / kTile;          // 128-row slabs: latency-bound, so favour many CTAs
+                                  const double* sgn, long strideSgn, int NP, int kb, double* v, double* x,
+                                  long v_stride, const ScfState* state, int batch, cudaStream_t stream) {
+    (void)NP;
+    int G = (kb * kTile) / kBackCols;   // 64 columns of the update per CTA
     if (G < 1) G = 1;
-    if (batch > 1 && G > 8) G = 8;               // batched frames already fill the machine
-    if (G > kBackMaxCtas) G = kBackMaxCtas;
-    while ((((rows + G - 1) / G + 63) & ~63) > kBackSlab) ++G;
     dim3 grid(G, 1, batch);
-    backsolve_step_kernel<<<grid, 256, 0, stream>>>(A, lda, strideA, Linv, strideLinv, sgn, strideSgn, NP, kb, v,
-                                                    v_stride, scratch, scratch_stride, counters, state);
+    backsolve_step_kernel<<<grid, 256, 0, stream>>>(A, lda, strideA, Linv, strideLinv, sgn, strideSgn, kb, v, x,
+                                                    v_stride, state);
     return cudaGetLastError();
 }
 

@@ -88,6 +88,8 @@ typedef struct cheq_stats {
     double gemm_ms;          /* sum of the launch durations */
     double gemm_flops;       /* algorithmic flops of those launches (2 m n k; n^2 k for the symmetric part) */
     uint64_t gemm_launches;
+    double potrf_ms;         /* same, diagonal-tile factorisation launches */
+    double backsolve_ms;     /* same, whole back substitutions */
 } cheq_stats;
 
 int32_t cheq_ctx_create(int32_t device, cheq_ctx** out);
@@ -167,6 +169,9 @@ int32_t cheq_dbg_gemm_nt(cheq_ctx* ctx, uint64_t m, uint64_t n, uint64_t k, cons
  * lower != 0 skips the tiles above the diagonal (the symmetric trailing update). */
 int32_t cheq_dbg_gemm_bench(cheq_ctx* ctx, uint64_t m, uint64_t n, uint64_t k, int32_t lower, int32_t subtract,
                             int32_t reps, double* ms_out);
+
+/* Plain FP64 FMA (non-tensor) throughput of the device in TFLOP/s: the ALU roofline of the STO assembly. */
+int32_t cheq_dbg_dfma_rate(cheq_ctx* ctx, double* tflops_out);
 
 /* Host-only: evaluates the STO pair table (built exactly as for the device) in fp64 on the CPU.  Used to
  * test the table construction without a GPU; not a solve path.  Distance in bohr, result in Hartree. */

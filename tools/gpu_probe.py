@@ -16,6 +16,7 @@ def main():
     P = get_default_parameters()
     ctx = cheq_b200.default_context(0)
     s = QEqSolver(P, SolverOptions(), ctx)
+    ctx._lib.cheq_set_profiling(ctx.handle, 1)
     for nm in sizes:
         Z, xyz = workloads.water_cluster(nm)
         chi, hard, rad, nq = workloads.gather_parameters(Z, P)
@@ -29,7 +30,9 @@ def main():
                   f"sumq={sum(r.charges):.2e} | host {st['ms_host_prepare']:.1f} h2d {st['ms_h2d']:.2f} "
                   f"asm {st['ms_assemble']:.2f} once {st['ms_factor_once']:.1f} scf {st['ms_scf']:.1f} "
                   f"d2h {st['ms_d2h']:.2f} launches {st['kernel_launches']} "
-                  f"TF/s {st['flops_factor']/((st['ms_factor_once']+st['ms_scf'])*1e9):.2f}", flush=True)
+                  f"TF/s {st['flops_factor']/((st['ms_factor_once']+st['ms_scf'])*1e9):.2f} | gemm {st['gemm_ms']:.1f} ms "
+                  f"({st['gemm_flops']/max(st['gemm_ms'],1e-9)/1e9:.1f} TF/s, {st['gemm_launches']} launches) potrf {st['potrf_ms']:.1f} ms "
+                  f"backsolve {st['backsolve_ms']:.1f} ms", flush=True)
 
 
 if __name__ == "__main__":
