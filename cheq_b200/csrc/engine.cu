@@ -112,6 +112,8 @@ struct cheq_ctx {
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;   // pairs (start, stop)
     std::vector<int> prof_cat;              // category of each pair: 0 GEMM, 1 diagonal-tile factorisation, 2 back substitution
+    struct ProfShape { int K, mt, nt; double flops; };
+    std::vector<ProfShape> prof_shape;      // GEMM shapes, for the optional launch log (env CHEQ_GEMM_LOG)
     size_t prof_used = 0;
     double prof_flops = 0.0;
 };
@@ -375,7 +377,11 @@ int launch_gemm_timed(cheq_ctx* ctx, const GemmArgs& g, int mt, int nt, int batc
     int rc = prof_begin(ctx, 0);
     if (rc) return rc;
     LAUNCH(launch_gemm_nt(g, mt, nt, batch, ctx->stream));
-    if (ctx->profile) ctx->prof_flops += flops * batch;
+    if (ctx->profile) {
+        ctx->prof_flops += flops * batch;
+        if (ctx->prof_shape.size() < ctx->prof_cat.size()) ctx->prof_shape.resize(ctx->prof_cat.size());
+        ctx->prof_shape[ctx->prof_used / 2] = {g.K, mt, nt, flops * batch};
+    }
     return prof_end(ctx);
 }
 
@@ -973,13 +979,21 @@ int solve_impl(cheq_ctx* ctx, const SolveIO& io) {
     if (ctx->profile) {
         double ms_sum[3] = {0.0, 0.0, 0.0};
         uint64_t n_gemm = 0;
+        FILE* log = nullptr;
+        if (const char* path = getenv("CHEQ_GEMM_LOG")) log = fopen(path, "w");
+        if (log) fprintf(log, "K,m_tiles,n_tiles,flops,ms\n");
         for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
             float ms = 0;
             cudaEventElapsedTime(&ms, ctx->prof_events[i], ctx->prof_events[i + 1]);
             const int cat = ctx->prof_cat[i / 2];
             ms_sum[cat] += ms;
             n_gemm += (cat == 0);
+            if (log && cat == 0) {
+                const auto& sh = ctx->prof_shape[i / 2];
+                fprintf(log, "%d,%d,%d,%.6e,%.6f\n", sh.K, sh.mt, sh.nt, sh.flops, ms);
+            }
         }
+        if (log) fclose(log);
         ctx->stats.gemm_ms = ms_sum[0];
         ctx->stats.gemm_launches = n_gemm;
         ctx->stats.gemm_flops = ctx->prof_flops;
@@ -1383,6 +1397,7 @@ int32_t cheq_dbg_gemm_bench(cheq_ctx* ctx, uint64_t m, uint64_t n, uint64_t k, i
     g.lower = lower & 1;
     g.subtract = subtract ? 1 : 0;
     if (lower & 0x30) set_gemm_warps((lower & 0x10) ? 8 : 16);   // debug: bit 4 -> 8 warps, bit 5 -> 16 warps
+    if (lower & 0xC0) set_gemm_warps((lower & 0x40) ? 64 : 128);  // debug: bit 6 -> 64-row tiles, bit 7 -> 128-row
     LAUNCH(launch_gemm_nt(g, (int)(m / kTile), (int)(n / kTile), 1, st));   // warm-up
     CU(cudaEventRecord(ctx->ev[0], st));
     for (int r = 0; r < reps; ++r) LAUNCH(launch_gemm_nt(g, (int)(m / kTile), (int)(n / kTile), 1, st));

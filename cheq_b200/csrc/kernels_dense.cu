@@ -56,11 +56,16 @@ constexpr int kGroupM = 8;   // tile rows per rasterisation group: their A slabs
 // scaling B fragments in the loop costs 4 % of DMMA throughput, a flagged branch 11 %); negative pivots are rare
 // (one per negative eigenvalue), so the epilogue applies  A S B^T = A B^T - 2 sum_{k: s_k = -1} a_k b_k^T  as
 // rank-1 corrections to the accumulators, driven by the per-tile lists the factorisation leaf writes.
-template <int FM>
-__global__ void __launch_bounds__((128 / (16 * FM)) * 4 * 32, 1) gemm_nt_kernel(GemmArgs g) {
-    constexpr int kWarpsM = 128 / (16 * FM);          // 2 or 4
+// FM = 16-row fragments per warp, WM = warps along M: CTA tile (16 FM WM) x 128.
+//   <4, 2>: 128 x 128, 8 warps (64 x 32 warp tiles)      <2, 4>: 128 x 128, 16 warps (32 x 32)
+//   <2, 2>:  64 x 128, 8 warps: twice the CTAs for skinny updates that would otherwise leave SMs idle
+template <int FM, int WM>
+__global__ void __launch_bounds__(WM * 4 * 32, 1) gemm_nt_kernel(GemmArgs g) {
+    constexpr int kWarpsM = WM;
     constexpr int kThreads = kWarpsM * 4 * 32;        // 256 or 512
-    constexpr int kChunks = 1024 / kThreads;          // 16-byte chunks per thread per operand per stage
+    constexpr int TM = 16 * FM * WM;                  // CTA tile rows: 128 or 64
+    constexpr int kChunksA = TM * 8 / kThreads;       // 16-byte chunks per thread per stage, A slab (TM x 16)
+    constexpr int kChunksB = 1024 / kThreads;         //                                      B slab (128 x 16)
     // grouped rasterisation: consecutive CTAs walk the tile columns of a group of kGroupM tile rows
     const int frame = blockIdx.z;
     int tile_m, tile_n;
@@ -73,15 +78,15 @@ __global__ void __launch_bounds__((128 / (16 * FM)) * 4 * 32, 1) gemm_nt_kernel(
         tile_n = rem / gsize;
         tile_m = first + (rem - tile_n * gsize);
     }
-    if (g.lower && tile_m < tile_n) return;
+    if (g.lower && tile_m * TM + TM - 1 < tile_n * BN) return;   // tile entirely above the diagonal
     if (g.state && !g.state[frame].active) return;
     extern __shared__ __align__(16) double smem[];
     double* As = smem;                          // [STAGES][BK][LDT]
     double* Bs = smem + STAGES * BK * LDT;      // [STAGES][BK][LDT]
 
-    const double* A = g.A + (long)frame * g.strideA + (long)tile_m * BM;
+    const double* A = g.A + (long)frame * g.strideA + (long)tile_m * TM;
     const double* B = g.B + (long)frame * g.strideB + (long)tile_n * BN;
-    double* C = g.C + (long)frame * g.strideC + (long)tile_m * BM + (long)tile_n * BN * g.ldc;
+    double* C = g.C + (long)frame * g.strideC + (long)tile_m * TM + (long)tile_n * BN * g.ldc;
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     const int wm = warp % kWarpsM, wn = warp / kWarpsM;   // kWarpsM x 4 warps, warp tile (16 FM) x 32
@@ -92,10 +97,15 @@ __global__ void __launch_bounds__((128 / (16 * FM)) * 4 * 32, 1) gemm_nt_kernel(
         double* bs = Bs + stage * BK * LDT;
         const long k0 = (long)ktile * BK;
 #pragma unroll
-        for (int i = 0; i < kChunks; ++i) {
+        for (int i = 0; i < kChunksA; ++i) {
+            const int c = t + i * kThreads;
+            const int kr = c / (TM / 2), mc = c % (TM / 2);
+            cp_async16(as + kr * LDT + 2 * mc, A + 2 * mc + (k0 + kr) * g.lda);
+        }
+#pragma unroll
+        for (int i = 0; i < kChunksB; ++i) {
             const int c = t + i * kThreads;   // 0..1023
             const int kr = c >> 6, mc = c & 63;
-            cp_async16(as + kr * LDT + 2 * mc, A + 2 * mc + (k0 + kr) * g.lda);
             cp_async16(bs + kr * LDT + 2 * mc, B + 2 * mc + (k0 + kr) * g.ldb);
         }
     };
@@ -585,8 +595,14 @@ cudaError_t launch_dfma_rate(double* out, int blocks, int iters, cudaStream_t st
     return cudaGetLastError();
 }
 
-int g_gemm_warps = 16;   // warps per GEMM CTA: 8 (64 x 32 warp tiles) or 16 (32 x 32)
-void set_gemm_warps(int w) { g_gemm_warps = (w == 8) ? 8 : 16; }
+int g_gemm_warps = 16;        // warps per 128 x 128 GEMM CTA: 8 (64 x 32 warp tiles) or 16 (32 x 32)
+int g_gemm_half_tiles = -1;   // -1: heuristic; 0 / 1: force 128- / 64-row tiles (tuning)
+void set_gemm_warps(int w) {
+    if (w == 8 || w == 16) g_gemm_warps = w;
+    if (w == 64) g_gemm_half_tiles = 1;
+    if (w == 128) g_gemm_half_tiles = 0;
+    if (w == 0) g_gemm_half_tiles = -1;
+}
 
 cudaError_t launch_gemm_nt(const GemmArgs& g, int m_tiles, int n_tiles, int batch, cudaStream_t stream) {
     if (m_tiles <= 0 || n_tiles <= 0) return cudaSuccess;
@@ -596,14 +612,26 @@ cudaError_t launch_gemm_nt(const GemmArgs& g, int m_tiles, int n_tiles, int batc
     dim3 grid(m_tiles * n_tiles, 1, batch);
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_nt_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+        cudaError_t e = cudaFuncSetAttribute(gemm_nt_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
         if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(gemm_nt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+            e = cudaFuncSetAttribute(gemm_nt_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(gemm_nt_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    if (g_gemm_warps == 8) gemm_nt_kernel<4><<<grid, 256, kGemmSmem, stream>>>(args);
-    else gemm_nt_kernel<2><<<grid, 512, kGemmSmem, stream>>>(args);
+    // skinny problems: 64-row tiles double the CTA count when 128-row tiles would leave SMs idle
+    const long tiles128 = g.lower ? (long)m_tiles * n_tiles - (long)n_tiles * (n_tiles - 1) / 2 : (long)m_tiles * n_tiles;
+    const bool half = (g_gemm_half_tiles < 0) ? (tiles128 * batch <= 74) : (g_gemm_half_tiles != 0);
+    if (half) {
+        args.m_tiles = 2 * m_tiles;
+        grid.x = 2 * m_tiles * n_tiles;
+        gemm_nt_kernel<2, 2><<<grid, 256, kGemmSmem, stream>>>(args);
+    } else if (g_gemm_warps == 8) {
+        gemm_nt_kernel<4, 2><<<grid, 256, kGemmSmem, stream>>>(args);
+    } else {
+        gemm_nt_kernel<2, 4><<<grid, 512, kGemmSmem, stream>>>(args);
+    }
     return cudaGetLastError();
 }
 

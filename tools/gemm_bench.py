@@ -37,16 +37,16 @@ def cublas(m, n, k, reps=5):
 
 def main():
     ctx = cheq_b200.default_context(0)
-    if sys.argv[1:] == ["warps"]:
-        r = C.c_double()
-        ctx._lib.cheq_dbg_dfma_rate(ctx.handle, C.byref(r))
-        print(f"plain DFMA rate: {r.value:.2f} TFLOP/s;", ctx.last_error(), flush=True)
-        return
-        for m, n, k, lower in [(8192, 8192, 8192, 0), (13568, 13440, 6784, 1), (13440, 1024, 1024, 1), (13440, 128, 128, 0)]:
-            for bit, w in ((0x10, 8), (0x20, 16)):
-                ms, tf = ours(ctx, m, n, k, lower | bit)
+    if sys.argv[1:] == ["tiles"]:
+        for m, n, k, lower in [(13440, 128, 128, 0), (6784, 128, 128, 0), (3328, 128, 128, 0), (13440, 256, 256, 1),
+                               (6784, 256, 128, 0), (6784, 384, 384, 1), (13440, 384, 384, 1), (6784, 896, 768, 1),
+                               (13440, 896, 768, 1), (6784, 1664, 1664, 1)]:
+            out = []
+            for bit, name in ((0x80, "128"), (0x40, "64")):
+                ms, _ = ours(ctx, m, n, k, lower | bit)
                 fl = 2.0 * m * n * k if not lower else (n * n * k + 2.0 * (m - n) * n * k)
-                print(f"m={m} n={n} k={k} lower={lower} warps={w}: {ms:8.3f} ms {fl / (ms * 1e-3) / 1e12:6.2f} TF/s", flush=True)
+                out.append(f"tile{name}: {ms * 1e3:8.1f} us {fl / (ms * 1e-3) / 1e12:6.2f} TF/s")
+            print(f"m={m:6d} n={n:5d} k={k:5d} lower={lower}  " + " | ".join(out), flush=True)
         return
     only = sys.argv[1:] == ["one"]
     shapes = [(8192, 8192, 8192, 0)] if only else [
