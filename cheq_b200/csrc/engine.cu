@@ -90,6 +90,61 @@ struct Layout {
 
 int round_up_tile(int v) { return ((v + kTile - 1) / kTile) * kTile; }
 
+// Where to split each panel of the recursive factorisation.  Halving is flop-optimal but the trailing update of a
+// panel is a grid of 128 x 128 tiles run in waves of 148 CTAs; a split one tile to the left or right can save a
+// whole wave of K = 128 n1 work.  cost() models a launch as waves x (K/16 x t_k + t_fixed) with the constants
+// measured on B200 (tools/gemm_bench.py), and a dynamic programme over (first tile, tile count) picks the splits.
+struct SplitPlan {
+    int mt_total = 0;   // tile rows of the trapezoid (NP / 128 + 1)
+    int batch = 1;
+    int nmax = 0;
+    std::vector<short> split;   // [j0t * (nmax + 1) + n] = tiles in the left part
+    std::vector<float> cost;
+    static double gemm_cost(long mt, long nt, long k_tiles, bool lower, int batch) {
+        long tiles = lower ? nt * (nt + 1) / 2 + (mt - nt) * nt : mt * nt;
+        if (tiles <= 0) return 0.0;
+        tiles *= batch;
+        const double ktiles16 = k_tiles * 8.0;
+        if (tiles <= 74) return std::ceil(2.0 * tiles / 148.0) * (ktiles16 * 1.25 + 8.0);
+        return std::ceil(tiles / 148.0) * (ktiles16 * 2.44 + 9.5);
+    }
+    void build(int mt_total_, int j_begin, int j_end, int batch_) {
+        // plan for panels inside tile columns [j_begin, j_end)
+        mt_total = mt_total_;
+        batch = batch_;
+        nmax = j_end;
+        split.assign((size_t)(nmax + 1) * (nmax + 1), 0);
+        cost.assign((size_t)(nmax + 1) * (nmax + 1), 0.0f);
+        const double leaf = 67.0;
+        for (int n = 1; n <= j_end - j_begin; ++n)
+            for (int j0 = j_begin; j0 + n <= j_end; ++j0) {
+                const size_t id = (size_t)j0 * (nmax + 1) + n;
+                if (n == 1) {
+                    cost[id] = (float)(leaf + gemm_cost(mt_total - j0 - 1, 1, 1, false, batch));
+                    continue;
+                }
+                double best = 1e30;
+                int arg = n / 2;
+                for (int n1 = 1; n1 < n; ++n1) {
+                    const double c = cost[(size_t)j0 * (nmax + 1) + n1] +
+                                     gemm_cost(mt_total - (j0 + n1), n - n1, n1, true, batch) +
+                                     cost[(size_t)(j0 + n1) * (nmax + 1) + (n - n1)];
+                    if (c < best - 1e-9) {
+                        best = c;
+                        arg = n1;
+                    }
+                }
+                cost[id] = (float)best;
+                split[id] = (short)arg;
+            }
+    }
+    int left_tiles(int j0t, int n) const {
+        if (j0t + n > nmax || split.empty()) return n / 2;
+        const int v = split[(size_t)j0t * (nmax + 1) + n];
+        return v > 0 ? v : n / 2;
+    }
+};
+
 }  // namespace
 
 struct cheq_ctx {
@@ -109,6 +164,7 @@ struct cheq_ctx {
     cudaEvent_t ev[8]{};
     uint64_t launches = 0;
     // optional per-launch timing of the dominant kernel (gemm_nt_kernel) with CUDA events on the stream
+    std::map<std::tuple<int, int, int, int>, SplitPlan> plans;   // (mt_total, j_begin, j_end, batch)
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;   // pairs (start, stop)
     std::vector<int> prof_cat;              // category of each pair: 0 GEMM, 1 diagonal-tile factorisation, 2 back substitution
@@ -348,7 +404,9 @@ struct Dense {
     int* neg_idx;       // [batch][NP / 128][128] their in-tile indices
     long strideNeg;
     double flops = 0.0;
+    const struct SplitPlan* plan = nullptr;   // wave-aware recursion splits (nullptr: halve)
 };
+
 
 // |pivot| below this (eV) is treated as a breakdown of the unpivoted factorisation -> pivoted-LU path.
 // Matrix entries are O(1..30) eV, so accepted pivots bound the element growth by ~1e5 (error ~1e-11).
@@ -383,6 +441,18 @@ int launch_gemm_timed(cheq_ctx* ctx, const GemmArgs& g, int mt, int nt, int batc
         ctx->prof_shape[ctx->prof_used / 2] = {g.K, mt, nt, flops * batch};
     }
     return prof_end(ctx);
+}
+
+const SplitPlan* get_plan(cheq_ctx* ctx, int MT, int j_begin, int j_end, int batch) {
+    if (j_end - j_begin < 2) return nullptr;
+    auto key = std::make_tuple(MT / kTile, j_begin / kTile, j_end / kTile, batch);
+    auto it = ctx->plans.find(key);
+    if (it == ctx->plans.end()) {
+        if (ctx->plans.size() > 64) ctx->plans.clear();
+        it = ctx->plans.emplace(key, SplitPlan()).first;
+        it->second.build(MT / kTile, j_begin / kTile, j_end / kTile, batch);
+    }
+    return &it->second;
 }
 
 // Recursive tall-panel Cholesky of columns [j0, j0 + n) with all rows down to MT (the rows below the panel are
@@ -420,7 +490,7 @@ int factor_panel(Dense& D, int j0, int n) {
         D.flops += (double)kTile * kTile * kTile / 3.0 + m * kTile * kTile;
         return CHEQ_OK;
     }
-    const int n1 = ((n / kTile) / 2) * kTile;
+    const int n1 = (D.plan ? D.plan->left_tiles(j0 / kTile, n / kTile) : (n / kTile) / 2) * kTile;
     int rc = factor_panel(D, j0, n1);
     if (rc) return rc;
     {
@@ -745,6 +815,7 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
 
     if (!L.scf) {
         // implementation.rs:284-292: one solve, iterations = 1, charges = raw solution
+        D.plan = get_plan(ctx, L.MT, 0, L.NP, batch);
         rc = factor_panel(D, 0, L.NP);
         if (rc) return rc;
         CU(cudaEventRecord(ctx->ev[3], st));
@@ -763,8 +834,10 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
 
     // geometry-invariant part: factor the non-hydrogen block, form the hydrogen Schur complement S0 and the
     // reduced right-hand sides; snapshot them.
+    D.plan = get_plan(ctx, L.MT, 0, L.nxp, batch);
     rc = factor_panel(D, 0, L.nxp);
     if (rc) return rc;
+    D.plan = get_plan(ctx, L.MT, L.nxp, L.NP, batch);
     rc = schur_update(D, L.nxp, L.nhp);
     if (rc) return rc;
     const long ld0 = L.MT - L.nxp;
