@@ -232,8 +232,25 @@ int find_or_add_type(std::vector<ElementType>& types, std::map<std::pair<uint8_t
 
 // Typing and ordering: non-hydrogen block first, then the n == 1 block (implementation.rs:475-477), each
 // sorted by element type so that warps of the assembly kernel see one pair type.
+// 30-bit Morton code of a position inside the bounding box: atoms of one element type are laid out along a
+// space-filling curve, so a 128 x 64 assembly tile pairs two compact groups of atoms and whole warps fall on
+// the same side of the integral's cutoff (far pairs skip the exponential).
+uint32_t morton30(double fx, double fy, double fz) {
+    auto spread = [](uint32_t v) {
+        v &= 0x3ff;
+        v = (v | (v << 16)) & 0x030000ff;
+        v = (v | (v << 8)) & 0x0300f00f;
+        v = (v | (v << 4)) & 0x030c30c3;
+        v = (v | (v << 2)) & 0x09249249;
+        return v;
+    };
+    auto q = [](double f) { return (uint32_t)std::min(1023.0, std::max(0.0, f * 1024.0)); };
+    return spread(q(fx)) | (spread(q(fy)) << 1) | (spread(q(fz)) << 2);
+}
+
 int make_layout(cheq_ctx* ctx, long n, const double* radius, const uint8_t* nq, bool hydrogen_scf,
-                const double* pc_radius, const uint8_t* pc_n, long m, Layout& L, std::vector<int>& pc_type) {
+                const double* pc_radius, const uint8_t* pc_n, long m, const double* xyz, Layout& L,
+                std::vector<int>& pc_type) {
     L.n = n;
     std::map<std::pair<uint8_t, uint64_t>, int> index;
     std::vector<int> atom_type(n);
@@ -250,7 +267,24 @@ int make_layout(cheq_ctx* ctx, long n, const double* radius, const uint8_t* nq, 
         if (L.scf && nq[i] == 1) hs.push_back((int)i);
         else xs.push_back((int)i);
     }
-    auto by_type = [&](int a, int b) { return atom_type[a] != atom_type[b] ? atom_type[a] < atom_type[b] : a < b; };
+    std::vector<uint32_t> code(n, 0);
+    if (xyz && n > 256) {
+        double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+        for (long i = 0; i < n; ++i)
+            for (int d = 0; d < 3; ++d) {
+                lo[d] = std::min(lo[d], xyz[3 * i + d]);
+                hi[d] = std::max(hi[d], xyz[3 * i + d]);
+            }
+        double ext = 1e-9;
+        for (int d = 0; d < 3; ++d) ext = std::max(ext, hi[d] - lo[d]);
+        for (long i = 0; i < n; ++i)
+            code[i] = morton30((xyz[3 * i] - lo[0]) / ext, (xyz[3 * i + 1] - lo[1]) / ext, (xyz[3 * i + 2] - lo[2]) / ext);
+    }
+    auto by_type = [&](int a, int b) {
+        if (atom_type[a] != atom_type[b]) return atom_type[a] < atom_type[b];
+        if (code[a] != code[b]) return code[a] < code[b];
+        return a < b;
+    };
     std::sort(xs.begin(), xs.end(), by_type);
     std::sort(hs.begin(), hs.end(), by_type);
     L.nx = (int)xs.size();
@@ -641,7 +675,14 @@ int prepare_and_assemble(cheq_ctx* ctx, const SolveIO& io, long frame0, int batc
             }
         }
         std::vector<int> pc_type;
-        int rc = make_layout(ctx, n, radius, nq, hydrogen_scf, pc_radius, pc_n, m, P.L, pc_type);
+        std::vector<double> h_xyz;
+        const double* xyz0 = io.xyz + frame0 * n * 3;   // first frame's geometry orders the atoms in space
+        if (io.device_ptrs) {
+            h_xyz.resize(3 * n);
+            CU(cudaMemcpy(h_xyz.data(), xyz0, (size_t)n * 24, cudaMemcpyDeviceToHost));
+            xyz0 = h_xyz.data();
+        }
+        int rc = make_layout(ctx, n, radius, nq, hydrogen_scf, pc_radius, pc_n, m, xyz0, P.L, pc_type);
         if (rc) return rc;
         PackedTables pk;
         rc = pack_tables(ctx, P.L.types, o.lambda_scale, o.basis, pk);

@@ -39,8 +39,9 @@ template <int BASIS>
 __device__ __forceinline__ double pair_value(const PairTableView& tb, int ti, int tj, double r2) {
     const int p = ti * tb.num_types + tj;
     if (r2 < tb.rzero2[p]) return tb.j0[p];
-    const double R = sqrt(r2);
-    const double rinv = 1.0 / R;
+    // 1/R and R from one rsqrt (1 ulp) instead of sqrt + divide: the far-pair path is then store-bound
+    const double rinv = rsqrt(r2);
+    const double R = r2 * rinv;
     if (BASIS == 0) {
         // gto.rs:82-90: erf(beta R) / R
         return kKe * rinv * erf(tb.beta[p] * R);
