@@ -311,6 +311,7 @@ struct PackedTables {
     std::vector<char> blob;
     PairTableView view{};   // pointers are OFFSETS into blob until rebased
     int pair_types = 0;
+    double rcut2_max = 0.0;  // STO: largest squared cutoff over all pair types [Angstrom^2]
 };
 
 // Builds the pair tables for all type pairs, in Angstrom units.
@@ -345,9 +346,11 @@ int pack_tables(cheq_ctx* ctx, const std::vector<ElementType>& types, double lam
                 // zeta == 0 or n == 0: undefined in the reference's dependency; propagate NaN
                 rzero2[p] = rzero2[pt] = 1e300;
                 j0[p] = j0[pt] = std::nan("");
+                out.rcut2_max = INFINITY;   // no fast path: the NaN must reach every pair of this type
                 continue;
             }
             rcut2[p] = rcut2[pt] = (tab.r_cut * B) * (tab.r_cut * B);
+            out.rcut2_max = std::max(out.rcut2_max, rcut2[p]);
             rzero2[p] = rzero2[pt] = (tab.r_zero * B) * (tab.r_zero * B);
             j0[p] = j0[pt] = tab.j0 * kHartreeToEv;
             term_begin[p] = term_begin[pt] = (int)term_c.size();
@@ -638,6 +641,7 @@ struct Prepared {
     Layout L;
     PairTableView view{};
     int blob_bytes = 0;
+    double rcut2_max = INFINITY;
     long strideA = 0;
     int batch = 1;
 };
@@ -691,6 +695,7 @@ int prepare_and_assemble(cheq_ctx* ctx, const SolveIO& io, long frame0, int batc
         rc = upload_tables(ctx, pk, P.view);
         if (rc) return rc;
         P.blob_bytes = (int)pk.blob.size();
+        P.rcut2_max = (o.basis == CHEQ_BASIS_STO) ? pk.rcut2_max : INFINITY;
         CU(ctx->perm.ensure(P.L.NP * sizeof(int)));
         CU(ctx->type.ensure(P.L.NP));
         CU(cudaMemcpyAsync(ctx->perm.p, P.L.perm.data(), P.L.NP * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -829,6 +834,7 @@ int prepare_and_assemble(cheq_ctx* ctx, const SolveIO& io, long frame0, int batc
     aa.a_stride = P.strideA;
     aa.pos_stride = L.NP;
     aa.NP = L.NP;
+    aa.rcut2_max = P.rcut2_max;
     LAUNCH(launch_assemble(aa, P.view, ctx->blob.as<char>(), P.blob_bytes, batch, st));
     LAUNCH(launch_rhs_rows(ctx->A.as<double>(), L.ld, P.strideA, L.NP, ctx->chi.as<double>(), d_vext, 0,
                            ctx->type.as<uint8_t>(), batch, st));

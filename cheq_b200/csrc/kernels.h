@@ -16,6 +16,7 @@ struct AssembleArgs {
     long ld, a_stride, pos_stride;
     int NP;
     int table_smem_bytes;      // filled by the launcher
+    double rcut2_max;          // STO: max over pair types of the squared cutoff [Angstrom^2] (inf disables)
 };
 
 struct VextArgs {

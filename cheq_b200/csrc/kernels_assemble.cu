@@ -110,13 +110,17 @@ assemble_lower_kernel(AssembleArgs a, PairTableView view, const char* blob, int 
         const int tjj = tj[jl];
         double v0 = 0.0, v1 = 0.0;
         if (tjj != kPadType) {
-            if (ti0 != kPadType) {
-                const double dx = xi0 - xj[jl], dy = yi0 - yj[jl], dz = zi0 - zj[jl];
-                v0 = pair_value<BASIS>(tb, ti0, tjj, dx * dx + dy * dy + dz * dz);
-            }
-            if (ti1 != kPadType) {
-                const double dx = xi1 - xj[jl], dy = yi1 - yj[jl], dz = zi1 - zj[jl];
-                v1 = pair_value<BASIS>(tb, ti1, tjj, dx * dx + dy * dy + dz * dz);
+            const double dx0 = xi0 - xj[jl], dy0 = yi0 - yj[jl], dz0 = zi0 - zj[jl];
+            const double dx1 = xi1 - xj[jl], dy1 = yi1 - yj[jl], dz1 = zi1 - zj[jl];
+            const double r20 = dx0 * dx0 + dy0 * dy0 + dz0 * dz0, r21 = dx1 * dx1 + dy1 * dy1 + dz1 * dz1;
+            // beyond every pair type's cutoff F(R) < 1e-19: J = kKe / R without touching the tables (with the
+            // space-filling-curve order most warps take this branch as a whole)
+            if (BASIS == 1 && r20 >= a.rcut2_max && r21 >= a.rcut2_max) {
+                v0 = (ti0 != kPadType) ? kKe * rsqrt(r20) : 0.0;
+                v1 = (ti1 != kPadType) ? kKe * rsqrt(r21) : 0.0;
+            } else {
+                if (ti0 != kPadType) v0 = pair_value<BASIS>(tb, ti0, tjj, r20);
+                if (ti1 != kPadType) v1 = pair_value<BASIS>(tb, ti1, tjj, r21);
             }
         }
         if (j == i0) v0 = d0;
