@@ -5,7 +5,10 @@ from __future__ import annotations
 import ctypes as C
 from pathlib import Path
 
-_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libcheq_b200.so"
+import os
+
+# CHEQ_B200_LIB selects an alternative build of the same library (kernel tuning experiments)
+_LIB_PATH = Path(os.environ.get("CHEQ_B200_LIB") or Path(__file__).resolve().parent / "lib" / "libcheq_b200.so")
 
 OK, NO_ATOMS, PARAMETER_NOT_FOUND, NOT_CONVERGED, LINALG, CUDA, INVALID_ARGUMENT, OUT_OF_MEMORY = range(8)
 

@@ -7,9 +7,9 @@
 // substitution is part of the factorisation.
 //
 // FP64 on Blackwell has no tcgen05 kind; the tensor path is mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4).  The
-// GEMM below stages 128 x 16 operand slabs with cp.async (LDGSTS) into padded shared memory (row stride
-// 132 doubles -> conflict-free 16-byte fragment loads), 4 stages, 8 warps each owning a 64 x 32 accumulator
-// tile (64 fp64 registers per thread), 32 DMMAs per 6 LDS.128.
+// GEMM below stages 128 x 32 operand slabs with cp.async (LDGSTS) into padded shared memory (row stride
+// 132 doubles -> conflict-free 16-byte fragment loads), 3 stages (203 KB), 16 warps each owning a 32 x 32
+// accumulator tile, 16 DMMAs per 4 LDS.128 (measured: 32-deep slabs +4 % over 16-deep x 4 stages).
 #include <cuda_runtime.h>
 
 #include "device_types.h"
@@ -21,7 +21,11 @@ namespace {
 // ------------------------------------------------------------------------------------------------------------
 // GEMM  C (-)= A * B^T,  A: m x K, B: n x K, column-major, all dimensions multiples of 128 (K of 16)
 // ------------------------------------------------------------------------------------------------------------
-constexpr int BM = 128, BN = 128, BK = 16, LDT = 132, STAGES = 4;
+#ifndef CHEQ_GEMM_BK
+#define CHEQ_GEMM_BK 32
+#define CHEQ_GEMM_STAGES 3
+#endif
+constexpr int BM = 128, BN = 128, BK = CHEQ_GEMM_BK, LDT = 132, STAGES = CHEQ_GEMM_STAGES;
 constexpr int kGemmThreads = 256;
 constexpr int kGemmSmem = STAGES * 2 * BK * LDT * (int)sizeof(double);  // 135168 B
 
@@ -64,8 +68,8 @@ __global__ void __launch_bounds__(WM * 4 * 32, 1) gemm_nt_kernel(GemmArgs g) {
     constexpr int kWarpsM = WM;
     constexpr int kThreads = kWarpsM * 4 * 32;        // 256 or 512
     constexpr int TM = 16 * FM * WM;                  // CTA tile rows: 128 or 64
-    constexpr int kChunksA = TM * 8 / kThreads;       // 16-byte chunks per thread per stage, A slab (TM x 16)
-    constexpr int kChunksB = 1024 / kThreads;         //                                      B slab (128 x 16)
+    constexpr int kChunksA = TM * BK / 2 / kThreads;  // 16-byte chunks per thread per stage, A slab (TM x BK)
+    constexpr int kChunksB = 64 * BK / kThreads;      //                                      B slab (128 x BK)
     // grouped rasterisation: consecutive CTAs walk the tile columns of a group of kGroupM tile rows
     const int frame = blockIdx.z;
     int tile_m, tile_n;
