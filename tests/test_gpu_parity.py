@@ -388,6 +388,24 @@ def test_batch_frames_parity(gpu_ctx, oracle):
 
 
 # ---- full size: properties that need no oracle -----------------------------------------------------------------
+def test_s100k_single_factorisation_properties(gpu_ctx, oracle):
+    """BASELINE config 5 size on ONE B200 (81 GB trapezoid): 100,002 atoms, one signed factorisation
+    (hydrogen_scf off keeps the test to ~15 s): neutrality and stationarity on sampled rows."""
+    Z, xyz = workloads.water_cluster(33334)
+    n = len(Z)
+    chi, hard, rad, nq = workloads.gather_parameters(Z, get_default_parameters())
+    s1 = QEqSolver(get_default_parameters(), SolverOptions(hydrogen_scf=False), gpu_ctx)
+    r = s1.solve_arrays(np.ascontiguousarray(xyz), chi, hard, rad, nq, 0.0)
+    q = np.array(r.charges)
+    assert r.iterations == 1 and abs(q.sum()) < 1e-7
+    rng = np.random.default_rng(2)
+    for i in rng.choice(n, size=12, replace=False):
+        d = np.linalg.norm(xyz - xyz[i], axis=1) / BOHR
+        row = np.array([oracle.sto_integral(d[j], int(nq[i]), rad[i] / BOHR, int(nq[j]), rad[j] / BOHR, 0.5) * EV
+                        if j != i else hard[i] for j in range(n)])
+        assert abs(chi[i] + row @ q + r.equilibrated_potential) < 1e-7
+
+
 def test_s20k_properties(gpu_ctx, oracle):
     """BASELINE headline size (20,001 atoms): neutrality, stationarity on sampled rows, permutation equivariance."""
     Z, xyz = workloads.water_20k()
