@@ -47,6 +47,11 @@ SIGNATURES = {
     "cheq_get_stats": (_I32, [_P, C.POINTER(Stats)]),
     "cheq_ctx_stream": (_P, [_P]),
     "cheq_set_profiling": (_I32, [_P, _I32]),
+    "cheq_dist_unique_id": (_I32, [_P]),
+    "cheq_ctx_dist_init": (_I32, [_P, _I32, _I32, _P]),
+    "cheq_ctx_dist_info": (_I32, [_P, C.POINTER(_I32), C.POINTER(_I32)]),
+    "cheq_set_factor_mode": (_I32, [_P, _I32, _I32]),
+    "cheq_dist_plan": (_I32, [_I32, _I32, _I32, _I32, _P, _P]),
     "cheq_solve": (_I32, [_P, _U64, _P, _P, _P, _P, _P, _D, C.POINTER(Options), C.POINTER(External), _P,
                           C.POINTER(_D), C.POINTER(C.c_uint32), C.POINTER(_D)]),
     "cheq_solve_device": (_I32, [_P, _U64, _P, _P, _P, _P, _P, _D, C.POINTER(Options), C.POINTER(External), _P,

@@ -9,10 +9,13 @@
 //      convergence logic run on the device, the host reads back one small record per iteration.
 // There is no CPU fallback: every numerical step is a kernel of kernels_*.cu.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstddef>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -147,9 +150,68 @@ struct SplitPlan {
 
 }  // namespace
 
+// Ownership of the column panels of one layout (distributed / look-ahead factorisation).
+// The X block (non-hydrogen) and the H block (n == 1 atoms) are cut separately into panels of `tpp` tile columns
+// (the last panel of a block may be narrower); panel p belongs to rank p % world (1-D block-cyclic).
+struct PanelPlan {
+    int nxt = -1, nht = -1, tpp = -1, world = -1, rank = -1;
+    std::vector<int> begin, end, owner;   // per panel, tile units
+    int x_panels = 0;                     // panels [0, x_panels) cover the X block
+    std::vector<int> own_tiles;           // tile columns owned by `rank`, ascending
+    std::vector<uint8_t> mask;            // per tile column: 1 = owned by `rank`
+    void build(int nxt_, int nht_, int tpp_, int world_, int rank_) {
+        nxt = nxt_; nht = nht_; tpp = tpp_; world = world_; rank = rank_;
+        begin.clear(); end.clear(); owner.clear(); own_tiles.clear();
+        mask.assign((size_t)nxt + nht, 0);
+        auto cut = [&](int t0, int t1) {
+            for (int t = t0; t < t1; t += tpp) {
+                begin.push_back(t);
+                end.push_back(std::min(t + tpp, t1));
+                owner.push_back((int)(owner.size() % (size_t)world));
+            }
+        };
+        cut(0, nxt);
+        x_panels = (int)begin.size();
+        cut(nxt, nxt + nht);
+        for (size_t p = 0; p < begin.size(); ++p)
+            if (owner[p] == rank)
+                for (int t = begin[p]; t < end[p]; ++t) {
+                    own_tiles.push_back(t);
+                    mask[t] = 1;
+                }
+    }
+};
+
+// NCCL entry points, resolved at run time (libnccl.so.2 is the one torch already loaded when the host process
+// initialised torch.distributed; the engine itself has no link-time dependency on it).
+struct NcclId { char internal[128]; };
+struct NcclApi {
+    void* handle = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+constexpr int kNcclChar = 0, kNcclInt = 2, kNcclDouble = 8, kNcclMax = 2;
+
 struct cheq_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t cur = nullptr;            // stream the factorisation kernels are launched on (stream or panel_stream)
+    // distributed / look-ahead factorisation
+    int rank = 0, world = 1;
+    void* comm = nullptr;                  // ncclComm_t
+    cudaStream_t panel_stream = nullptr;   // high priority: panel factorisation + broadcasts
+    cudaEvent_t ev_ready = nullptr, ev_bcast = nullptr;
+    int factor_mode = 0;                   // 0: auto (recursive on one GPU, blocked when world > 1), 1: blocked
+    int tiles_per_panel = 4;
+    PanelPlan pplan;
+    DeviceBuffer stage, own_list, col_mask;
+    double ms_comm_host = 0.0;
     std::mutex mu;
     std::string err;
     std::map<TableKey, StoPairTable> sto_cache;
@@ -458,12 +520,12 @@ int prof_begin(cheq_ctx* ctx, int category) {
     }
     if (ctx->prof_cat.size() < ctx->prof_events.size() / 2) ctx->prof_cat.resize(ctx->prof_events.size() / 2);
     ctx->prof_cat[ctx->prof_used / 2] = category;
-    CU(cudaEventRecord(ctx->prof_events[ctx->prof_used], ctx->stream));
+    CU(cudaEventRecord(ctx->prof_events[ctx->prof_used], ctx->cur));
     return CHEQ_OK;
 }
 int prof_end(cheq_ctx* ctx) {
     if (!ctx->profile) return CHEQ_OK;
-    CU(cudaEventRecord(ctx->prof_events[ctx->prof_used + 1], ctx->stream));
+    CU(cudaEventRecord(ctx->prof_events[ctx->prof_used + 1], ctx->cur));
     ctx->prof_used += 2;
     return CHEQ_OK;
 }
@@ -471,7 +533,7 @@ int prof_end(cheq_ctx* ctx) {
 int launch_gemm_timed(cheq_ctx* ctx, const GemmArgs& g, int mt, int nt, int batch, double flops) {
     int rc = prof_begin(ctx, 0);
     if (rc) return rc;
-    LAUNCH(launch_gemm_nt(g, mt, nt, batch, ctx->stream));
+    LAUNCH(launch_gemm_nt(g, mt, nt, batch, ctx->cur));
     if (ctx->profile) {
         ctx->prof_flops += flops * batch;
         if (ctx->prof_shape.size() < ctx->prof_cat.size()) ctx->prof_shape.resize(ctx->prof_cat.size());
@@ -502,7 +564,7 @@ int factor_panel(Dense& D, int j0, int n) {
         double* Lk = D.Linv + (long)(j0 / kTile) * kTile * kTile;
         if (int rcp = prof_begin(ctx, 1)) return rcp;
         LAUNCH(launch_potrf_tile(Ajj, D.ld, D.strideA, Lk, D.strideLinv, D.sgn + j0, D.strideSgn, D.neg_cnt + j0 / kTile,
-                                 D.neg_idx + (long)j0, D.strideNeg, D.state, kPivotTol, D.batch, ctx->stream));
+                                 D.neg_idx + (long)j0, D.strideNeg, D.state, kPivotTol, D.batch, ctx->cur));
         if (int rcp = prof_end(ctx)) return rcp;
         const int mt = (D.MT - j0 - kTile) / kTile;
         if (mt > 0) {
@@ -594,8 +656,187 @@ int backsolve(Dense& D, int NP, double* v, double* x, long v_stride) {
     if (int rcp = prof_begin(ctx, 2)) return rcp;
     for (int kb = NP / kTile - 1; kb >= 0; --kb)
         LAUNCH(launch_backsolve_step(D.A, D.ld, D.strideA, D.Linv, D.strideLinv, D.sgn, D.strideSgn, NP, kb, v, x,
-                                     v_stride, D.state, D.batch, ctx->stream));
+                                     v_stride, D.state, D.batch, ctx->cur));
     return prof_end(ctx);
+}
+
+// ---- NCCL (run-time binding) ---------------------------------------------------------------------------------
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+
+bool nccl_load(std::string& err) {
+    std::lock_guard<std::mutex> lock(g_nccl_mu);
+    if (g_nccl.handle) return true;
+    std::vector<std::string> names;
+    if (const char* env = getenv("CHEQ_NCCL_LIB")) names.push_back(env);
+    names.push_back("libnccl.so.2");
+    names.push_back("libnccl.so");
+    void* h = nullptr;
+    for (const std::string& nm : names) {
+        h = dlopen(nm.c_str(), RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+    }
+    if (!h) {
+        err = std::string("cannot load NCCL (set CHEQ_NCCL_LIB): ") + (dlerror() ? dlerror() : "");
+        return false;
+    }
+    NcclApi api;
+    auto sym = [&](const char* name) {
+        void* f = dlsym(h, name);
+        if (!f) err = std::string("NCCL symbol missing: ") + name;
+        return f;
+    };
+    api.GetUniqueId = (int (*)(void*))sym("ncclGetUniqueId");
+    api.CommInitRank = (int (*)(void**, int, NcclId, int))sym("ncclCommInitRank");
+    api.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
+    api.Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclBroadcast");
+    api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclAllReduce");
+    api.GroupStart = (int (*)())sym("ncclGroupStart");
+    api.GroupEnd = (int (*)())sym("ncclGroupEnd");
+    api.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
+    if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.Broadcast || !api.AllReduce ||
+        !api.GroupStart || !api.GroupEnd || !api.GetErrorString)
+        return false;
+    api.handle = h;
+    g_nccl = api;
+    return true;
+}
+
+#define NC(call)                                                                              \
+    do {                                                                                      \
+        int r__ = (call);                                                                     \
+        if (r__ != 0) {                                                                       \
+            ctx->err = std::string(#call) + ": " + g_nccl.GetErrorString(r__);                \
+            return CHEQ_ERR_CUDA;                                                             \
+        }                                                                                     \
+    } while (0)
+
+// Panel plan of a layout for this context's (rank, world); uploads the owned-tile list and the ownership mask.
+int ensure_panel_plan(cheq_ctx* ctx, const Layout& L) {
+    const int nxt = (L.scf ? L.nxp : L.NP) / kTile, nht = (L.scf ? L.nhp : 0) / kTile;
+    PanelPlan& pp = ctx->pplan;
+    if (pp.nxt == nxt && pp.nht == nht && pp.tpp == ctx->tiles_per_panel && pp.world == ctx->world &&
+        pp.rank == ctx->rank)
+        return CHEQ_OK;
+    pp.build(nxt, nht, ctx->tiles_per_panel, ctx->world, ctx->rank);
+    CU(ctx->own_list.ensure(std::max<size_t>(4, pp.own_tiles.size() * sizeof(int))));
+    CU(ctx->col_mask.ensure(std::max<size_t>(4, pp.mask.size())));
+    CU(cudaStreamSynchronize(ctx->stream));   // earlier kernels may still read the previous plan's arrays
+    if (!pp.own_tiles.empty())
+        CU(cudaMemcpy(ctx->own_list.p, pp.own_tiles.data(), pp.own_tiles.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ctx->col_mask.p, pp.mask.data(), pp.mask.size(), cudaMemcpyHostToDevice));
+    return CHEQ_OK;
+}
+
+// Trailing update by the factored panel [j0, j0 + n):  C[:, cols] -= W S W[cols]^T for `count` owned tile columns
+// (absolute indices in the device list `list`, host copy `hlist`), rows from tile e down to MT.
+int update_columns(Dense& D, int j0, int n, int e, const int* list, const int* hlist, int count) {
+    if (count <= 0) return CHEQ_OK;
+    cheq_ctx* ctx = D.ctx;
+    const int MTt = D.MT / kTile;
+    GemmArgs g{};
+    g.A = D.A + (long)e * kTile + (long)j0 * D.ld;
+    g.lda = D.ld;
+    g.strideA = D.strideA;
+    g.B = D.A + (long)j0 * D.ld;
+    g.ldb = D.ld;
+    g.strideB = D.strideA;
+    g.C = D.A + (long)e * kTile;
+    g.ldc = D.ld;
+    g.strideC = D.strideA;
+    g.K = n;
+    g.lower = 1;
+    g.subtract = 1;
+    g.neg_cnt = D.neg_cnt + j0 / kTile;
+    g.neg_idx = D.neg_idx + (long)j0;
+    g.strideNeg = D.strideNeg;
+    g.state = D.state;
+    g.n_list = list;
+    g.row0 = e * kTile;
+    double fl = 0.0;
+    for (int i = 0; i < count; ++i)
+        fl += (double)n * kTile * kTile * (2.0 * (MTt - hlist[i]) - 1.0);   // diagonal tile: symmetric half
+    const int rc = launch_gemm_timed(ctx, g, MTt - e, count, D.batch, fl);
+    if (rc) return rc;
+    D.flops += fl;
+    return CHEQ_OK;
+}
+
+// Right-looking factorisation of panels [p_begin, p_end) of the plan with one-panel look-ahead:
+//   panel stream (high priority): the owner factors panel p (recursive tall-panel kernel sequence), the panel, its
+//     diagonal-tile inverses and pivot signs are broadcast to all ranks (NCCL over NVLink), non-owners store it;
+//   main stream: every rank updates its own tile columns to the right of the panel; the columns of panel p + 1
+//     go first, so that its owner can start factoring while the rest of the update is still running.
+// Afterwards every rank holds the complete factor L, the forward-substituted right-hand-side rows and (for the
+// columns it owns) the updated trailing matrix.  One GPU (world == 1): the same schedule without broadcasts.
+int factor_blocked(Dense& D, int p_begin, int p_end) {
+    cheq_ctx* ctx = D.ctx;
+    const PanelPlan& pp = ctx->pplan;
+    cudaStream_t ms = ctx->stream, ps = ctx->panel_stream;
+    const int* d_list = ctx->own_list.as<int>();
+    // nothing on the panel stream (factorisation, received panels) may overtake what the main stream has queued
+    CU(cudaEventRecord(ctx->ev_ready, ms));
+    CU(cudaStreamWaitEvent(ps, ctx->ev_ready, 0));
+    for (int p = p_begin; p < p_end; ++p) {
+        const int j0 = pp.begin[p] * kTile, n = (pp.end[p] - pp.begin[p]) * kTile;
+        const long rows = D.MT - j0;
+        const bool mine = pp.owner[p] == ctx->rank;
+        if (mine) {
+            CU(cudaStreamWaitEvent(ps, ctx->ev_ready, 0));
+            const SplitPlan* saved = D.plan;
+            D.plan = nullptr;   // panels are a few tiles wide: plain halving
+            ctx->cur = ps;
+            const int rc = factor_panel(D, j0, n);
+            ctx->cur = ms;
+            D.plan = saved;
+            if (rc) return rc;
+        }
+        if (ctx->world > 1) {
+            auto t0 = Clock::now();
+            double* stage = ctx->stage.as<double>();
+            double* Ap = D.A + (long)j0 + (long)j0 * D.ld;
+            if (mine)
+                CU(cudaMemcpy2DAsync(stage, rows * 8, Ap, D.ld * 8, rows * 8, n, cudaMemcpyDeviceToDevice, ps));
+            double* Lk = D.Linv + (long)(j0 / kTile) * kTile * kTile;
+            const int root = pp.owner[p];
+            NC(g_nccl.GroupStart());
+            NC(g_nccl.Broadcast(stage, stage, (size_t)rows * n, kNcclDouble, root, ctx->comm, ps));
+            NC(g_nccl.Broadcast(Lk, Lk, (size_t)n * kTile, kNcclDouble, root, ctx->comm, ps));
+            NC(g_nccl.Broadcast(D.sgn + j0, D.sgn + j0, (size_t)n, kNcclDouble, root, ctx->comm, ps));
+            NC(g_nccl.Broadcast(D.neg_cnt + j0 / kTile, D.neg_cnt + j0 / kTile, (size_t)n / kTile, kNcclInt, root,
+                                ctx->comm, ps));
+            NC(g_nccl.Broadcast(D.neg_idx + j0, D.neg_idx + j0, (size_t)n, kNcclInt, root, ctx->comm, ps));
+            NC(g_nccl.GroupEnd());
+            if (!mine)
+                CU(cudaMemcpy2DAsync(Ap, D.ld * 8, stage, rows * 8, rows * 8, n, cudaMemcpyDeviceToDevice, ps));
+            ctx->launches += 1;
+            ctx->ms_comm_host += ms_since(t0);
+        }
+        CU(cudaEventRecord(ctx->ev_bcast, ps));
+        CU(cudaStreamWaitEvent(ms, ctx->ev_bcast, 0));
+        // trailing update of the owned tile columns right of the panel
+        const int e = pp.end[p];
+        const int pos = (int)(std::lower_bound(pp.own_tiles.begin(), pp.own_tiles.end(), e) - pp.own_tiles.begin());
+        const int cnt = (int)pp.own_tiles.size() - pos;
+        const bool next_mine = (p + 1 < p_end) && pp.owner[p + 1] == ctx->rank;
+        int head = 0;
+        if (next_mine) {
+            head = pp.end[p + 1] - pp.begin[p + 1];
+            const int rc = update_columns(D, j0, n, e, d_list + pos, pp.own_tiles.data() + pos, head);
+            if (rc) return rc;
+            CU(cudaEventRecord(ctx->ev_ready, ms));
+        }
+        const int rc = update_columns(D, j0, n, e, d_list + pos + head, pp.own_tiles.data() + pos + head, cnt - head);
+        if (rc) return rc;
+    }
+    if (ctx->world > 1) {
+        // a pivot breakdown seen by one owner must stop every rank
+        int* info = (int*)((char*)D.state + offsetof(ScfState, info));
+        NC(g_nccl.AllReduce(info, info, 1, kNcclInt, kNcclMax, ctx->comm, ps));
+        CU(cudaEventRecord(ctx->ev_bcast, ps));
+        CU(cudaStreamWaitEvent(ms, ctx->ev_bcast, 0));
+    }
+    return CHEQ_OK;
 }
 
 int ensure_host_state(cheq_ctx* ctx, size_t batch) {
@@ -646,8 +887,12 @@ struct Prepared {
     int batch = 1;
 };
 
+bool use_blocked(const cheq_ctx* ctx, int batch) {
+    return batch == 1 && (ctx->world > 1 || ctx->factor_mode == 1);
+}
+
 int prepare_and_assemble(cheq_ctx* ctx, const SolveIO& io, long frame0, int batch, bool hydrogen_scf,
-                         Prepared& P, bool topology_ready) {
+                         Prepared& P, bool topology_ready, bool all_columns = false) {
     const long n = io.n;
     const cheq_options& o = *io.opt;
     cudaStream_t st = ctx->stream;
@@ -835,6 +1080,12 @@ int prepare_and_assemble(cheq_ctx* ctx, const SolveIO& io, long frame0, int batc
     aa.pos_stride = L.NP;
     aa.NP = L.NP;
     aa.rcut2_max = P.rcut2_max;
+    if (use_blocked(ctx, batch)) {
+        // distributed assembly: every rank produces only the tile columns it owns
+        rc = ensure_panel_plan(ctx, L);
+        if (rc) return rc;
+        if (ctx->world > 1 && !all_columns) aa.col_mask = ctx->col_mask.as<uint8_t>();
+    }
     LAUNCH(launch_assemble(aa, P.view, ctx->blob.as<char>(), P.blob_bytes, batch, st));
     LAUNCH(launch_rhs_rows(ctx->A.as<double>(), L.ld, P.strideA, L.NP, ctx->chi.as<double>(), d_vext, 0,
                            ctx->type.as<uint8_t>(), batch, st));
@@ -859,11 +1110,20 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
     double* xs = ctx->xsol.as<double>();
     double* q = ctx->q.as<double>();
     int rc;
+    const bool blocked = use_blocked(ctx, batch);
+    const bool dist = blocked && ctx->world > 1;
+    const PanelPlan& pp = ctx->pplan;
+    if (dist) CU(ctx->stage.ensure((size_t)L.MT * ctx->tiles_per_panel * kTile * 8));
+    const uint8_t* mask_h = dist ? ctx->col_mask.as<uint8_t>() + L.nxp / kTile : nullptr;
 
     if (!L.scf) {
         // implementation.rs:284-292: one solve, iterations = 1, charges = raw solution
-        D.plan = get_plan(ctx, L.MT, 0, L.NP, batch);
-        rc = factor_panel(D, 0, L.NP);
+        if (blocked) {
+            rc = factor_blocked(D, 0, (int)pp.begin.size());
+        } else {
+            D.plan = get_plan(ctx, L.MT, 0, L.NP, batch);
+            rc = factor_panel(D, 0, L.NP);
+        }
         if (rc) return rc;
         CU(cudaEventRecord(ctx->ev[3], st));
         LAUNCH(launch_mu(D.A, D.ld, D.strideA, L.NP, io.total_charge, v, L.NP, D.sgn, D.strideSgn, D.state, batch, st));
@@ -881,18 +1141,25 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
 
     // geometry-invariant part: factor the non-hydrogen block, form the hydrogen Schur complement S0 and the
     // reduced right-hand sides; snapshot them.
-    D.plan = get_plan(ctx, L.MT, 0, L.nxp, batch);
-    rc = factor_panel(D, 0, L.nxp);
-    if (rc) return rc;
-    D.plan = get_plan(ctx, L.MT, L.nxp, L.NP, batch);
-    rc = schur_update(D, L.nxp, L.nhp);
-    if (rc) return rc;
+    if (blocked) {
+        // right-looking over the X panels: the trailing updates reach into the owned hydrogen columns, which
+        // therefore hold the Schur complement when the last X panel is done
+        rc = factor_blocked(D, 0, pp.x_panels);
+        if (rc) return rc;
+    } else {
+        D.plan = get_plan(ctx, L.MT, 0, L.nxp, batch);
+        rc = factor_panel(D, 0, L.nxp);
+        if (rc) return rc;
+        D.plan = get_plan(ctx, L.MT, L.nxp, L.NP, batch);
+        rc = schur_update(D, L.nxp, L.nhp);
+        if (rc) return rc;
+    }
     const long ld0 = L.MT - L.nxp;
     const long stride0 = ld0 * L.nhp;
     double* Ahh = D.A + (long)L.nxp + (long)L.nxp * L.ld;
     const int mt_h = (L.MT - L.nxp) / kTile, nt_h = L.nhp / kTile;
     LAUNCH(launch_copy_lower_tiles(Ahh, L.ld, D.strideA, ctx->S0.as<double>(), ld0, stride0, mt_h, nt_h, nullptr,
-                                   batch, st));
+                                   batch, st, mask_h));
     CU(cudaEventRecord(ctx->ev[3], st));
     const double flops_once = D.flops;
     D.flops = 0.0;
@@ -904,11 +1171,11 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
     for (it = 1; it <= o.max_iterations; ++it) {
         if (it > 1)
             LAUNCH(launch_copy_lower_tiles(ctx->S0.as<double>(), ld0, stride0, Ahh, L.ld, D.strideA, mt_h, nt_h,
-                                           D.state, batch, st));
+                                           D.state, batch, st, mask_h));
         LAUNCH(launch_set_h_diagonal(Ahh, L.ld, D.strideA, ctx->S0.as<double>(), ld0, stride0, hard_h,
                                      q + L.nxp, L.NP, type_h, L.nhp, D.state, batch, st));
         D.flops = 0.0;
-        rc = factor_panel(D, L.nxp, L.nhp);
+        rc = blocked ? factor_blocked(D, pp.x_panels, (int)pp.begin.size()) : factor_panel(D, L.nxp, L.nhp);
         if (rc) return rc;
         LAUNCH(launch_mu(D.A, D.ld, D.strideA, L.NP, io.total_charge, v, L.NP, D.sgn, D.strideSgn, D.state, batch, st));
         rc = backsolve(D, L.NP, v, xs, L.NP);
@@ -916,7 +1183,22 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
         LAUNCH(launch_scf_mix(xs, q, L.NP, ctx->type.as<uint8_t>(), L.NP, D.state, batch, st));
         CU(cudaMemsetAsync(ctx->active.p, 0, sizeof(int), st));
         LAUNCH(launch_scf_decide(D.state, o.tolerance, o.damping_kind, batch, ctx->active.as<int>(), st));
-        CU(cudaMemcpyAsync(ctx->h_active, ctx->active.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        if (dist) {
+            // every rank solved the same replicated triangular systems; rank 0's iterate and decision are made
+            // authoritative so that the control flow of all ranks stays in lock-step
+            cudaStream_t ps = ctx->panel_stream;
+            CU(cudaEventRecord(ctx->ev_ready, st));
+            CU(cudaStreamWaitEvent(ps, ctx->ev_ready, 0));
+            NC(g_nccl.GroupStart());
+            NC(g_nccl.Broadcast(D.state, D.state, sizeof(ScfState), kNcclChar, 0, ctx->comm, ps));
+            NC(g_nccl.Broadcast(ctx->active.p, ctx->active.p, sizeof(int), kNcclChar, 0, ctx->comm, ps));
+            NC(g_nccl.Broadcast(q, q, (size_t)L.NP, kNcclDouble, 0, ctx->comm, ps));
+            NC(g_nccl.GroupEnd());
+            CU(cudaMemcpyAsync(ctx->h_active, ctx->active.p, sizeof(int), cudaMemcpyDeviceToHost, ps));
+            CU(cudaStreamSynchronize(ps));
+        } else {
+            CU(cudaMemcpyAsync(ctx->h_active, ctx->active.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        }
         CU(cudaStreamSynchronize(st));
         flops_iter_total += D.flops * (double)batch;   // upper bound for batches (finished frames skip)
         if (*ctx->h_active == 0) break;
@@ -1068,7 +1350,7 @@ int solve_impl(cheq_ctx* ctx, const SolveIO& io) {
             if (ctx->h_state[f].info != 0) not_spd.push_back(f);
         if (batch == 1 && !not_spd.empty()) {
             // single solve: redo with the pivoted LU
-            rc = prepare_and_assemble(ctx, io, f0, 1, io.opt->hydrogen_scf != 0, P, true);
+            rc = prepare_and_assemble(ctx, io, f0, 1, io.opt->hydrogen_scf != 0, P, true, true);
             if (rc) return rc;
             rc = lu_scf(ctx, io, P);
             if (rc) return rc;
@@ -1080,7 +1362,7 @@ int solve_impl(cheq_ctx* ctx, const SolveIO& io) {
         if (rc) return rc;
         // batched frames that were not positive definite: one LU solve each, results overwrite the frame's slots
         for (int f : not_spd) {
-            rc = prepare_and_assemble(ctx, io, f0 + f, 1, io.opt->hydrogen_scf != 0, P, true);
+            rc = prepare_and_assemble(ctx, io, f0 + f, 1, io.opt->hydrogen_scf != 0, P, true, true);
             if (rc) return rc;
             rc = lu_scf(ctx, io, P);
             if (rc) return rc;
@@ -1151,6 +1433,17 @@ int32_t cheq_ctx_create(int32_t device, cheq_ctx** out) {
             delete ctx;
             return CHEQ_ERR_CUDA;
         }
+    ctx->cur = ctx->stream;
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithPriority(&ctx->panel_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_bcast, cudaEventDisableTiming) != cudaSuccess) {
+        delete ctx;
+        return CHEQ_ERR_CUDA;
+    }
+    if (const char* env = getenv("CHEQ_FACTOR_MODE")) ctx->factor_mode = atoi(env) == 1 ? 1 : 0;
+    if (const char* env = getenv("CHEQ_TILES_PER_PANEL")) ctx->tiles_per_panel = std::max(1, std::min(64, atoi(env)));
     *out = ctx;
     return CHEQ_OK;
 }
@@ -1159,6 +1452,14 @@ void cheq_ctx_destroy(cheq_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->panel_stream) cudaStreamSynchronize(ctx->panel_stream);
+    if (ctx->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm);
+    ctx->stage.release();
+    ctx->own_list.release();
+    ctx->col_mask.release();
+    if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
+    if (ctx->ev_bcast) cudaEventDestroy(ctx->ev_bcast);
+    if (ctx->panel_stream) cudaStreamDestroy(ctx->panel_stream);
     DeviceBuffer* bufs[] = {&ctx->in_xyz, &ctx->in_chi, &ctx->in_hard, &ctx->in_radius, &ctx->in_nq, &ctx->perm,
                             &ctx->type, &ctx->x, &ctx->y, &ctx->z, &ctx->diag, &ctx->chi, &ctx->hard, &ctx->vext,
                             &ctx->A, &ctx->S0, &ctx->Linv, &ctx->v, &ctx->q, &ctx->scratch, &ctx->counters,
@@ -1202,6 +1503,65 @@ int32_t cheq_set_profiling(cheq_ctx* ctx, int32_t enabled) {
     if (!ctx) return CHEQ_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(ctx->mu);
     ctx->profile = enabled != 0;
+    return CHEQ_OK;
+}
+
+int32_t cheq_dist_unique_id(uint8_t* id_out) {
+    if (!id_out) return CHEQ_ERR_INVALID_ARGUMENT;
+    std::string err;
+    if (!nccl_load(err)) return CHEQ_ERR_CUDA;
+    NcclId id;
+    if (g_nccl.GetUniqueId(&id) != 0) return CHEQ_ERR_CUDA;
+    std::memcpy(id_out, id.internal, CHEQ_DIST_ID_BYTES);
+    return CHEQ_OK;
+}
+
+int32_t cheq_ctx_dist_init(cheq_ctx* ctx, int32_t rank, int32_t world, const uint8_t* id) {
+    if (!ctx) return CHEQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->err.clear();
+    if (world < 1 || rank < 0 || rank >= world || (world > 1 && !id))
+        return fail(ctx, CHEQ_ERR_INVALID_ARGUMENT, "invalid rank / world / id");
+    if (ctx->comm) return fail(ctx, CHEQ_ERR_INVALID_ARGUMENT, "context is already part of a group");
+    if (world == 1) return CHEQ_OK;
+    if (!nccl_load(ctx->err)) return CHEQ_ERR_CUDA;
+    CU(cudaSetDevice(ctx->device));
+    NcclId nid;
+    std::memcpy(nid.internal, id, CHEQ_DIST_ID_BYTES);
+    void* comm = nullptr;
+    NC(g_nccl.CommInitRank(&comm, world, nid, rank));
+    ctx->comm = comm;
+    ctx->rank = rank;
+    ctx->world = world;
+    ctx->pplan = PanelPlan();
+    return CHEQ_OK;
+}
+
+int32_t cheq_ctx_dist_info(const cheq_ctx* ctx, int32_t* rank_out, int32_t* world_out) {
+    if (!ctx) return CHEQ_ERR_INVALID_ARGUMENT;
+    if (rank_out) *rank_out = ctx->rank;
+    if (world_out) *world_out = ctx->world;
+    return CHEQ_OK;
+}
+
+int32_t cheq_set_factor_mode(cheq_ctx* ctx, int32_t mode, int32_t tiles_per_panel) {
+    if (!ctx || mode < 0 || mode > 1 || tiles_per_panel < 0 || tiles_per_panel > 64) return CHEQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->factor_mode = mode;
+    if (tiles_per_panel > 0) ctx->tiles_per_panel = tiles_per_panel;
+    return CHEQ_OK;
+}
+
+int32_t cheq_dist_plan(int32_t x_tiles, int32_t h_tiles, int32_t tiles_per_panel, int32_t world,
+                       int32_t* tile_owner_out, int32_t* tile_panel_out) {
+    if (x_tiles < 0 || h_tiles < 0 || tiles_per_panel < 1 || world < 1) return CHEQ_ERR_INVALID_ARGUMENT;
+    PanelPlan pp;
+    pp.build(x_tiles, h_tiles, tiles_per_panel, world, 0);
+    for (size_t p = 0; p < pp.begin.size(); ++p)
+        for (int t = pp.begin[p]; t < pp.end[p]; ++t) {
+            if (tile_owner_out) tile_owner_out[t] = pp.owner[p];
+            if (tile_panel_out) tile_panel_out[t] = (int32_t)p;
+        }
     return CHEQ_OK;
 }
 
@@ -1339,7 +1699,7 @@ int32_t cheq_assemble_matrix(cheq_ctx* ctx, uint64_t n_atoms, const double* xyz,
     io.nq = n_quantum;
     io.opt = &o;
     Prepared P;
-    int rc = prepare_and_assemble(ctx, io, 0, 1, true, P, false);
+    int rc = prepare_and_assemble(ctx, io, 0, 1, true, P, false, true);
     if (rc) return rc;
     const long n = (long)n_atoms;
     CU(ctx->misc0.ensure((size_t)n * n * 8));
@@ -1386,7 +1746,7 @@ int32_t cheq_external_potential(cheq_ctx* ctx, uint64_t n_atoms, const double* x
         for (long i = 0; i < n; ++i) v_out[i] = 0.0;
         return CHEQ_OK;
     }
-    int rc = prepare_and_assemble(ctx, io, 0, 1, false, P, false);
+    int rc = prepare_and_assemble(ctx, io, 0, 1, false, P, false, true);
     if (rc) return rc;
     CU(ctx->out_q.ensure(n * 8));
     LAUNCH(launch_scatter_charges(P.L.NP, ctx->perm.as<int>(), ctx->vext.as<double>(), P.L.NP,

@@ -17,6 +17,7 @@ struct AssembleArgs {
     int NP;
     int table_smem_bytes;      // filled by the launcher
     double rcut2_max;          // STO: max over pair types of the squared cutoff [Angstrom^2] (inf disables)
+    const uint8_t* col_mask;   // nullable, one flag per 128-column tile: 0 = another rank assembles this tile column
 };
 
 struct VextArgs {
@@ -56,6 +57,11 @@ struct GemmArgs {
     long strideNeg;            // per frame, in tiles
     int m_tiles, n_tiles;      // filled by the launcher
     const ScfState* state;     // nullable; frames with active == 0 are skipped
+    // Column-list mode (distributed / look-ahead updates): tile column t of the grid is tile column n_list[t] of
+    // C and of B; B and C then point at absolute tile column 0 and row0 is the absolute row of C's first row
+    // (used by the `lower` test).  nullptr: identity.
+    const int* n_list;
+    int row0;
 };
 
 int assemble_smem_bytes(int table_bytes, int* table_smem_bytes);
@@ -84,9 +90,10 @@ cudaError_t launch_potrf_tile(double* A, long lda, long strideA, double* Linv, l
                               long strideSgn, int* neg_cnt, int* neg_idx, long strideNeg, ScfState* state,
                               double pivot_tol, int batch, cudaStream_t stream);
 // copies the tiles on/below the diagonal of an (m_tiles x n_tiles) tile region
+// col_mask (nullable): one flag per tile column of the region, 0 = skip (columns owned by another rank)
 cudaError_t launch_copy_lower_tiles(const double* src, long lds, long stride_src, double* dst, long ldd,
                                     long stride_dst, int m_tiles, int n_tiles, const ScfState* state, int batch,
-                                    cudaStream_t stream);
+                                    cudaStream_t stream, const uint8_t* col_mask = nullptr);
 // A_ii = S0_ii + hardness_i * kHChargeFactor * clamp(q_i, -0.95, 0.95) for the real atoms of the hydrogen block
 cudaError_t launch_set_h_diagonal(double* A, long lda, long strideA, const double* S0, long ld0, long stride0,
                                   const double* hard_h, const double* q_h, long q_stride, const uint8_t* type_h,

@@ -78,6 +78,7 @@ assemble_lower_kernel(AssembleArgs a, PairTableView view, const char* blob, int 
     extern __shared__ __align__(16) char smem_raw[];
     const int bi = blockIdx.x, bj = blockIdx.y, frame = blockIdx.z;
     if (bi * kAsmRows + kAsmRows - 1 < bj * kAsmCols) return;  // tile strictly above the diagonal
+    if (a.col_mask && !a.col_mask[(bj * kAsmCols) / kTile]) return;   // tile column assembled by another rank
     double* xj = (double*)smem_raw;
     double* yj = xj + kAsmCols;
     double* zj = yj + kAsmCols;

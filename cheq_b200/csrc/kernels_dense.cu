@@ -12,6 +12,8 @@
 // accumulator tile, 16 DMMAs per 4 LDS.128 (measured: 32-deep slabs +4 % over 16-deep x 4 stages).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "device_types.h"
 #include "kernels.h"
 
@@ -82,7 +84,8 @@ __global__ void __launch_bounds__(WM * 4 * 32, 1) gemm_nt_kernel(GemmArgs g) {
         tile_n = rem / gsize;
         tile_m = first + (rem - tile_n * gsize);
     }
-    if (g.lower && tile_m * TM + TM - 1 < tile_n * BN) return;   // tile entirely above the diagonal
+    if (g.n_list) tile_n = g.n_list[tile_n];                     // column-list mode: absolute tile column
+    if (g.lower && g.row0 + tile_m * TM + TM - 1 < tile_n * BN) return;   // tile entirely above the diagonal
     if (g.state && !g.state[frame].active) return;
     extern __shared__ __align__(16) double smem[];
     double* As = smem;                          // [STAGES][BK][LDT]
@@ -358,11 +361,260 @@ potrf_tile_kernel(double* A_, long lda, long strideA, double* Minv_, long stride
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Diagonal tile, DMMA-blocked variant (experimental, see launch_potrf_tile).  Same mathematics and outputs as potrf_tile_kernel, but the tile
+// is held in registers in DMMA accumulator layout (warp w owns tile rows 2w, 2w+1 of the 16 x 16 grid of 8 x 8
+// tiles; lane T holds rows T/4, columns 2 (T%4), +1 of each) and eliminated four columns at a time:
+//   (a) the owners write the current 128 x 4 panel to shared memory;
+//   (c) warp 0 runs the four pivots on it (lane l holds rows l, l+32, l+64, l+96), producing the final panel, the
+//       scaled columns u_k and the pivot signs;
+//   (e) every warp applies the rank-4 update  e(r, c) -= sum_k s_k u_k[r] u_k[c]  with one DMMA.8x8x4 per 8 x 8
+//       tile (A fragment = -s u rows, B fragment = u columns), skipping finished columns and the dead part of X;
+//       diagonal tiles keep their not-yet-started X entries by a lane mask, and the one tile that contains the
+//       panel itself is updated with predicated scalar FMAs.
+// Element semantics as above: (r >= c) holds A -> L, (r < c) holds X[c][r], X = L^-1; update iff c > k and
+// (r >= c or r <= k).
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884_acc(double (&c)[2], double a, double b) { dmma884(c[0], c[1], a, b); }
+
+// 1/sqrt(x) for x in the range of pivots (1e-30 .. 1e30): single-precision seed + two Newton steps in fp64
+// (23 -> 46 -> 53+ bits).  No library call: the CUDA rsqrt() keeps a slow-path subroutine that forces the
+// register-resident tile through a stack frame.
+__device__ __forceinline__ double rsqrt_pivot(double x) {
+    double y = (double)rsqrtf((float)x);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double t = x * y;
+        const double h = fma(-t, y, 1.0);
+        y = fma(0.5 * y, h, y);
+    }
+    return y;
+}
+
+template <int TCB, int HALF>
+__device__ __forceinline__ void potrf3_step(double (&c)[2][16][2], int warp, int lane, double (*Pn)[kTile],
+                                            double (*Pk)[kTile], double (*Ut)[kTile], double* sg4, double* dinv,
+                                            double* sg, ScfState* state, int frame, double pivot_tol) {
+    constexpr int k0 = 8 * TCB + 4 * HALF;
+    const int g = lane >> 2, q = lane & 3;
+    const bool owns_panel = (q >> 1) == HALF;     // this lane's column pair of tile column TCB lies in the panel
+    const int pj = (q & 1) * 2;                   // panel column of its first element
+    if (owns_panel) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int r = 16 * warp + 8 * t + g;
+            Pn[pj][r] = c[t][TCB][0];
+            Pn[pj + 1][r] = c[t][TCB][1];
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double p[4][4];   // [slot][column]: row = lane + 32 slot
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) p[s][j] = Pn[j][lane + 32 * s];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            constexpr int dummy = 0;
+            (void)dummy;
+            const int k = k0 + j;
+            const int ks = k >> 5, kl = k & 31;   // compile-time: slot and lane that hold row k
+            const double d = __shfl_sync(0xffffffffu, p[ks][j], kl);
+            const double ad = fabs(d);
+            const bool bad = !(ad > pivot_tol) || !(ad < 1.0e30);
+            const double sgnk = (d < 0.0) ? -1.0 : 1.0;
+            double il = bad ? 1.0 : rsqrt_pivot(ad);
+            double l = bad ? 1.0 : ad * il;
+            if (!bad) {
+                const double res = fma(-l, l, ad);
+                l = fma(0.5 * il, res, l);
+                il = fma(fma(-l, il, 1.0), il, il);
+            }
+            const double sil = sgnk * il;
+            if (lane == 0) {
+                dinv[k] = il;
+                sg[k] = sgnk;
+                sg4[j] = sgnk;
+                if (bad && state) atomicExch(&state[frame].info, k + 1);
+            }
+            double u[4];
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const int r = lane + 32 * s;
+                const double v = p[s][j];
+                double uu = v * sil, keep = (r > k) ? uu : v * il;
+                if (r == k) {
+                    uu = sil;
+                    keep = l;
+                }
+                p[s][j] = keep;
+                u[s] = uu;
+                Ut[j][r] = uu;
+            }
+            // the remaining columns of the panel
+#pragma unroll
+            for (int jj = j + 1; jj < 4; ++jj) {
+                const int cc = k0 + jj;
+                const double ucj = __shfl_sync(0xffffffffu, u[cc >> 5], cc & 31);
+                const double f = -sgnk * ucj;
+#pragma unroll
+                for (int s = 0; s < 4; ++s) {
+                    const int r = lane + 32 * s;
+                    if (r >= cc || r <= k) p[s][jj] = fma(f, u[s], p[s][jj]);
+                }
+            }
+        }
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) Pk[j][lane + 32 * s] = p[s][j];
+    }
+    __syncthreads();
+    if (owns_panel) {
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int r = 16 * warp + 8 * t + g;
+            c[t][TCB][0] = Pk[pj][r];
+            c[t][TCB][1] = Pk[pj + 1][r];
+        }
+    }
+    // rank-4 update: lane's A element is (row 8 tr + g, pivot k0 + q), its B element (pivot k0 + q, column 8 tc + g)
+    const double sq = sg4[q];
+    double a[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const int tr = 2 * warp + t;
+        const int r = 8 * tr + g;
+        a[t] = -sq * Ut[q][r];
+        if (tr == TCB && r > k0 + q) a[t] = 0.0;   // rows of the panel's tile row below pivot k0+q act as X rows (zero)
+    }
+#pragma unroll
+    for (int tc = TCB; tc < 16; ++tc) {
+        if (tc == TCB && HALF == 1) continue;      // no column of this tile column lies beyond the panel
+        const int cb = 8 * tc + g;
+        const double b = (cb > k0 + 3) ? Ut[q][cb] : 0.0;
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            const int tr = 2 * warp + t;
+            if (tr < TCB) {
+                dmma884_acc(c[t][tc], a[t], b);                     // X rows above the panel
+            } else if (tr == TCB) {
+                if (tc > TCB) dmma884_acc(c[t][tc], a[t], b);       // X rows inside the panel's tile row
+            } else if (tc < tr) {
+                dmma884_acc(c[t][tc], a[t], b);                     // L part
+            } else if (tc == tr) {                                  // diagonal tile: L part only (g >= column)
+                double d0 = c[t][tc][0], d1 = c[t][tc][1];
+                dmma884(d0, d1, a[t], b);
+                c[t][tc][0] = (g >= 2 * q) ? d0 : c[t][tc][0];
+                c[t][tc][1] = (g >= 2 * q + 1) ? d1 : c[t][tc][1];
+            }
+        }
+    }
+    // the tile that contains the panel: columns beyond the panel exist only for the first half
+    if (HALF == 0 && warp == TCB / 2) {
+        constexpr int t = TCB % 2;
+        const int r = 8 * TCB + g;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int cc = 8 * TCB + 2 * q + e;
+            if (cc > k0 + 3) {
+                double v = c[t][TCB][e];
+#pragma unroll
+                for (int kp = 0; kp < 4; ++kp)
+                    if (r >= cc || r <= k0 + kp) v = fma(-sg4[kp] * Ut[kp][r], Ut[kp][cc], v);
+                c[t][TCB][e] = v;
+            }
+        }
+    }
+}
+
+template <int TCB>
+__device__ __forceinline__ void potrf3_block(double (&c)[2][16][2], int warp, int lane, double (*Pn)[kTile],
+                                             double (*Pk)[kTile], double (*Ut)[kTile], double* sg4, double* dinv,
+                                             double* sg, ScfState* state, int frame, double pivot_tol) {
+    potrf3_step<TCB, 0>(c, warp, lane, Pn, Pk, Ut, sg4, dinv, sg, state, frame, pivot_tol);
+    potrf3_step<TCB, 1>(c, warp, lane, Pn, Pk, Ut, sg4, dinv, sg, state, frame, pivot_tol);
+}
+
+__global__ void __launch_bounds__(kPotrfThreads)
+potrf_tile_dmma_kernel(double* A_, long lda, long strideA, double* Minv_, long strideM, double* sgn_, long strideSgn,
+                       int* neg_cnt_, int* neg_idx_, long strideNeg, ScfState* state, double pivot_tol) {
+    const int frame = blockIdx.z;
+    if (state && !state[frame].active) return;
+    extern __shared__ __align__(16) double Ms[];   // staging of M for a coalesced store
+    __shared__ double Pn[4][kTile], Pk[4][kTile], Ut[4][kTile];
+    __shared__ double dinv[kTile], sg[kTile], sg4[4];
+    double* A = A_ + (long)frame * strideA;
+    double* Minv = Minv_ + (long)frame * strideM;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int g = lane >> 2, q = lane & 3;
+
+    double c[2][16][2];
+#pragma unroll
+    for (int tt = 0; tt < 2; ++tt)
+#pragma unroll
+        for (int tc = 0; tc < 16; ++tc)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int r = 16 * warp + 8 * tt + g, cc = 8 * tc + 2 * q + e;
+                c[tt][tc][e] = (r >= cc) ? A[r + (long)cc * lda] : 0.0;
+            }
+
+    potrf3_block<0>(c, warp, lane, Pn, Pk, Ut, sg4, dinv, sg, state, frame, pivot_tol);
+    potrf3_block<1>(c, warp, lane, Pn, Pk, Ut, sg4, dinv, sg, state, frame, pivot_tol);
+    potrf3_block<2>(c, warp, lane, Pn, Pk, Ut, sg4, dinv, sg, state, frame, pivot_tol);
+    potrf3_block<3>(c, warp, lane, Pn, Pk, Ut, sg4, dinv, sg, state, frame, pivot_tol);
+    potrf3_block<4>(c, warp, lane, Pn, Pk, Ut, sg4, dinv, sg, state, frame, pivot_tol);
+    potrf3_block<5>(c, warp, lane, Pn, Pk, Ut, sg4, dinv, sg, state, frame, pivot_tol);
+    potrf3_block<6>(c, warp, lane, Pn, Pk, Ut, sg4, dinv, sg, state, frame, pivot_tol);
+    potrf3_block<7>(c, warp, lane, Pn, Pk, Ut, sg4, dinv, sg, state, frame, pivot_tol);
+    potrf3_block<8>(c, warp, lane, Pn, Pk, Ut, sg4, dinv, sg, state, frame, pivot_tol);
+    potrf3_block<9>(c, warp, lane, Pn, Pk, Ut, sg4, dinv, sg, state, frame, pivot_tol);
+    potrf3_block<10>(c, warp, lane, Pn, Pk, Ut, sg4, dinv, sg, state, frame, pivot_tol);
+    potrf3_block<11>(c, warp, lane, Pn, Pk, Ut, sg4, dinv, sg, state, frame, pivot_tol);
+    potrf3_block<12>(c, warp, lane, Pn, Pk, Ut, sg4, dinv, sg, state, frame, pivot_tol);
+    potrf3_block<13>(c, warp, lane, Pn, Pk, Ut, sg4, dinv, sg, state, frame, pivot_tol);
+    potrf3_block<14>(c, warp, lane, Pn, Pk, Ut, sg4, dinv, sg, state, frame, pivot_tol);
+    potrf3_block<15>(c, warp, lane, Pn, Pk, Ut, sg4, dinv, sg, state, frame, pivot_tol);
+    __syncthreads();
+
+    // L back to global; M = S X staged through shared memory (Ms[j * ld + i] = M[i][j])
+#pragma unroll
+    for (int tt = 0; tt < 2; ++tt)
+#pragma unroll
+        for (int tc = 0; tc < 16; ++tc)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int r = 16 * warp + 8 * tt + g, cc = 8 * tc + 2 * q + e;
+                const double v = c[tt][tc][e];
+                if (r >= cc) A[r + (long)cc * lda] = v;
+                double m = 0.0;
+                if (r < cc) m = sg[cc] * v;
+                else if (r == cc) m = sg[r] * dinv[r];
+                Ms[r * kPotrfLd + cc] = m;
+            }
+    __syncthreads();
+    for (int idx = t; idx < kTile * kTile; idx += kPotrfThreads) {
+        const int i = idx & (kTile - 1), j = idx >> 7;
+        Minv[idx] = Ms[j * kPotrfLd + i];
+    }
+    if (t < kTile && sgn_) sgn_[(long)frame * strideSgn + t] = sg[t];
+    if (t == 0 && neg_cnt_) {
+        int n = 0;
+        int* idx = neg_idx_ + (long)frame * strideNeg * kTile;
+        for (int i = 0; i < kTile; ++i)
+            if (sg[i] < 0.0) idx[n++] = i;
+        neg_cnt_[(long)frame * strideNeg] = n;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 copy_lower_tiles_kernel(const double* src, long lds, long stride_src, double* dst, long ldd, long stride_dst,
-                        const ScfState* state) {
+                        const ScfState* state, const uint8_t* col_mask) {
     const int ti = blockIdx.x, tj = blockIdx.y, frame = blockIdx.z;
     if (ti < tj) return;
+    if (col_mask && !col_mask[tj]) return;
     if (state && !state[frame].active) return;
     const double* s = src + (long)frame * stride_src + (long)ti * kTile + (long)tj * kTile * lds;
     double* d = dst + (long)frame * stride_dst + (long)ti * kTile + (long)tj * kTile * ldd;
@@ -643,24 +895,37 @@ cudaError_t launch_potrf_tile(double* A, long lda, long strideA, double* Linv, l
                               long strideSgn, int* neg_cnt, int* neg_idx, long strideNeg, ScfState* state,
                               double pivot_tol, int batch, cudaStream_t stream) {
     static bool configured = false;
+    // CHEQ_POTRF_DMMA=1 selects the rank-4 DMMA variant.  Measured on B200 (profiles/r1_potrf_variants.txt): it is
+    // 2x SLOWER than the rank-1 DFMA kernel (132 vs 66 us per tile) because ptxas keeps part of the 128-register
+    // tile in local memory (512 B stack frame), so the DFMA kernel stays the default.
+    static bool use_scalar = true;
     if (!configured) {
         cudaError_t e =
             cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPotrfSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(potrf_tile_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPotrfSmem);
         if (e != cudaSuccess) return e;
+        const char* env = getenv("CHEQ_POTRF_DMMA");
+        use_scalar = !(env && env[0] == '1');
         configured = true;
     }
     dim3 grid(1, 1, batch);
-    potrf_tile_kernel<<<grid, kPotrfThreads, kPotrfSmem, stream>>>(A, lda, strideA, Linv, strideLinv, sgn, strideSgn,
-                                                                   neg_cnt, neg_idx, strideNeg, state, pivot_tol);
+    if (use_scalar)
+        potrf_tile_kernel<<<grid, kPotrfThreads, kPotrfSmem, stream>>>(A, lda, strideA, Linv, strideLinv, sgn, strideSgn,
+                                                                       neg_cnt, neg_idx, strideNeg, state, pivot_tol);
+    else
+        potrf_tile_dmma_kernel<<<grid, kPotrfThreads, kPotrfSmem, stream>>>(A, lda, strideA, Linv, strideLinv, sgn,
+                                                                            strideSgn, neg_cnt, neg_idx, strideNeg,
+                                                                            state, pivot_tol);
     return cudaGetLastError();
 }
 
 cudaError_t launch_copy_lower_tiles(const double* src, long lds, long stride_src, double* dst, long ldd,
                                     long stride_dst, int m_tiles, int n_tiles, const ScfState* state, int batch,
-                                    cudaStream_t stream) {
+                                    cudaStream_t stream, const uint8_t* col_mask) {
     if (m_tiles <= 0 || n_tiles <= 0) return cudaSuccess;
     dim3 grid(m_tiles, n_tiles, batch);
-    copy_lower_tiles_kernel<<<grid, 256, 0, stream>>>(src, lds, stride_src, dst, ldd, stride_dst, state);
+    copy_lower_tiles_kernel<<<grid, 256, 0, stream>>>(src, lds, stride_src, dst, ldd, stride_dst, state, col_mask);
     return cudaGetLastError();
 }
 

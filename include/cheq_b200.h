@@ -102,6 +102,28 @@ void* cheq_ctx_stream(const cheq_ctx* ctx);
 /* Per-launch CUDA-event timing of the dominant kernel (off by default; adds two event records per launch). */
 int32_t cheq_set_profiling(cheq_ctx* ctx, int32_t enabled);
 
+/* ---- multi-GPU: one dense system across the GPUs of a node ----------------------------
+ * The reference is single-node CPU code (rayon, implementation.rs:394, 491) and has no equivalent; this is the
+ * "distributed factorisation with NCCL panel broadcasts" row of the scope table.  One process per GPU.  Rank 0
+ * obtains an id with cheq_dist_unique_id, the host runtime hands the 128 bytes to every rank (torch.distributed,
+ * MPI, a file ...), and every rank calls cheq_ctx_dist_init on its own context.  From then on cheq_solve /
+ * cheq_solve_device on that context are COLLECTIVE for single-frame calls: all ranks must call them with
+ * identical inputs; the matrix columns are assembled and updated by their owners (1-D block-cyclic panels), each
+ * factored panel is broadcast over NVLink, and every rank returns the same charges.  cheq_solve_batch stays
+ * local (frames are independent: shard them across ranks instead). */
+#define CHEQ_DIST_ID_BYTES 128
+int32_t cheq_dist_unique_id(uint8_t* id_out /* CHEQ_DIST_ID_BYTES */);
+int32_t cheq_ctx_dist_init(cheq_ctx* ctx, int32_t rank, int32_t world, const uint8_t* id);
+int32_t cheq_ctx_dist_info(const cheq_ctx* ctx, int32_t* rank_out, int32_t* world_out);
+/* Factorisation schedule: mode 0 = automatic (recursive tall-panel on one GPU, right-looking panels with
+ * look-ahead when the context is part of a group), 1 = right-looking panels with look-ahead also on one GPU.
+ * tiles_per_panel: panel width in 128-column tiles (0 keeps the current value; default 4). */
+int32_t cheq_set_factor_mode(cheq_ctx* ctx, int32_t mode, int32_t tiles_per_panel);
+/* Host-only: the owner rank and panel index of every 128-column tile for a layout with x_tiles non-hydrogen and
+ * h_tiles hydrogen tile columns (arrays of x_tiles + h_tiles entries, either may be NULL). */
+int32_t cheq_dist_plan(int32_t x_tiles, int32_t h_tiles, int32_t tiles_per_panel, int32_t world,
+                       int32_t* tile_owner_out, int32_t* tile_panel_out);
+
 /*
  * QEqSolver::solve / solve_in_field after element lookup.  `external` may be NULL or empty
  * (types.rs:281-286) for a vacuum solve.  On CHEQ_OK and on CHEQ_ERR_NOT_CONVERGED the outputs hold the

@@ -387,6 +387,27 @@ def test_batch_frames_parity(gpu_ctx, oracle):
     assert np.max(np.abs(np.array(single.charges) - q[2])) < 1e-12
 
 
+@pytest.mark.parametrize("tpp", [1, 3, 4])
+def test_blocked_lookahead_schedule_single_gpu(gpu_ctx, oracle, tpp):
+    """The right-looking panel schedule with look-ahead (the multi-GPU factorisation, run on one GPU without
+    broadcasts) gives the same answer as the oracle and as the recursive schedule."""
+    ctx = cheq_b200.Context(0)
+    assert ctx._lib.cheq_set_factor_mode(ctx.handle, 1, tpp) == 0
+    Z, xyz = workloads.water_cluster(375)
+    for kw in ({}, {"hydrogen_scf": False}, {"basis_type": BasisType.Gto}):
+        o = SolverOptions(**kw)
+        res = QEqSolver(get_default_parameters(), o, ctx).solve(atoms_of(Z, xyz), 0.0)
+        assert_parity(res, oracle.solve(Z, xyz, 0.0, oracle_opts(oracle, o)))
+        rec = QEqSolver(get_default_parameters(), o, gpu_ctx).solve(atoms_of(Z, xyz), 0.0)
+        assert np.max(np.abs(np.array(res.charges) - np.array(rec.charges))) < 1e-10
+    c = [c for g in __import__("json").loads((__import__("pathlib").Path(__file__).parent / "golden" /
+                                              "rappe_goddard.json").read_text())["groups"] for c in g["cases"]
+         if c["name"] == "C2H4"][0]
+    res = solver(ctx).solve(atoms_of(c["Z"], c["xyz"]), 0.0)
+    assert_parity(res, oracle.solve(c["Z"], np.array(c["xyz"])))
+    ctx.close()
+
+
 # ---- full size: properties that need no oracle -----------------------------------------------------------------
 def test_s100k_single_factorisation_properties(gpu_ctx, oracle):
     """BASELINE config 5 size on ONE B200 (81 GB trapezoid): 100,002 atoms, one signed factorisation
