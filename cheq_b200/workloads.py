@@ -147,6 +147,34 @@ def water_20k(seed: int = SEED):
     return water_cluster(6667, seed)
 
 
+def solvated_100k(n_solute: int = 10000, n_waters: int = 30000, seed: int = SEED, spacing: float = 3.1,
+                  jitter: float = 0.15, clearance: float = 2.6):
+    """S100k (BASELINE config 5): an `n_solute`-atom organic chain (C/H/N/O) solvated by the `n_waters` lattice
+    waters closest to it (oxygen at least `clearance` Angstrom from every solute atom) -> 100,000 atoms.
+    Returns (Z, xyz); solute atoms first, then O, H, H per water."""
+    from scipy.spatial import cKDTree
+    Zs, xs = organic_chain(n_solute, seed)
+    rng = np.random.default_rng(seed + 7)
+    lo, hi = xs.min(axis=0) - 12.0, xs.max(axis=0) + 12.0
+    axes = [np.arange(lo[d], hi[d], spacing) for d in range(3)]
+    grid = np.stack(np.meshgrid(*axes, indexing="ij"), axis=-1).reshape(-1, 3)
+    dist, _ = cKDTree(xs).query(grid)
+    ok = np.where(dist >= clearance + jitter * math.sqrt(3.0))[0]
+    if len(ok) < n_waters:
+        raise ValueError("water lattice too small")
+    keep = ok[np.argsort(dist[ok], kind="stable")[:n_waters]]
+    keep.sort()
+    centers = grid[keep] + rng.uniform(-jitter, jitter, size=(n_waters, 3))
+    r_oh, ang = 0.9572, math.radians(104.52)
+    local = np.array([[0.0, 0.0, 0.0],
+                      [r_oh * math.sin(ang / 2), 0.0, r_oh * math.cos(ang / 2)],
+                      [-r_oh * math.sin(ang / 2), 0.0, r_oh * math.cos(ang / 2)]])
+    R = _random_rotations(rng, n_waters)
+    xw = (centers[:, None, :] + np.einsum("mij,aj->mai", R, local)).reshape(-1, 3)
+    Z = list(Zs) + [8, 1, 1] * n_waters
+    return Z, np.vstack([xs, xw])
+
+
 def gather_parameters(Z, parameters):
     """Z -> (chi, hardness, radius, n) arrays using a cheq_b200.Parameters (host-side element lookup)."""
     el = parameters.elements
