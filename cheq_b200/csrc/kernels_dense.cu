@@ -609,6 +609,174 @@ potrf_tile_dmma_kernel(double* A_, long lda, long strideA, double* Minv_, long s
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Diagonal tile, shared-memory blocked variant (default).  Same outputs as potrf_tile_kernel.
+//
+// The 128 x 128 tile lives in shared memory, T[c * 129 + r]; as in the rank-1 kernel the lower part (r >= c)
+// becomes L and the strict upper part (r < c) holds X[c][r], X = L^-1 (forward elimination of the identity).
+// Columns are eliminated in blocks of 16 (block K = columns c0 .. c0 + 15):
+//   A  one warp factors the 16 x 16 diagonal block in registers (lane i = row c0 + i, pivots exchanged by shuffle):
+//      D = L_D S_D L_D^T, X_D = L_D^-1.  This is the only place with a per-pivot dependency chain
+//      (shuffle -> rsqrt -> scale -> update); nothing else in the CTA waits on individual pivots.
+//   B  every other row r (L rows below the block, X rows above it) is transformed by the block inverse,
+//      n_r = e(r, K) X_D^T; L rows store s_j n_r[j], X rows n_r[j]; W[j][r] = n_r[j] for all rows (for the rows
+//      of the block itself W[j][r] = X_D[j][r]).
+//   C  rank-16 update of the L-shaped region right of the block: e(r, c) -= sum_j W[j][r] L[c][j] for
+//      c > c0 + 15 and (r >= c or r < c0 + 16), in 4 x 4 register tiles (rows strided by 32 so that shared-memory
+//      accesses are conflict-free, W rows kept in registers across column tiles).
+// ------------------------------------------------------------------------------------------------------------
+// One pivot of the 16 x 16 diagonal block held by a warp (lane i = row i, e[j] = column j); recursion on the
+// compile-time pivot index keeps e[] in registers.
+template <int k>
+__device__ __forceinline__ void pb_pivot(double (&e)[16], double& myil, int i, int lane, int c0, double* dinv,
+                                         double* sg, ScfState* state, int frame, double pivot_tol) {
+    const double d = __shfl_sync(0xffffffffu, e[k], k);
+    const double ad = fabs(d);
+    const bool bad = !(ad > pivot_tol) || !(ad < 1.0e30);
+    const double sgnk = (d < 0.0) ? -1.0 : 1.0;
+    const double il = bad ? 1.0 : rsqrt_pivot(ad);
+    const double l = bad ? 1.0 : ad * il;
+    const double sil = sgnk * il;
+    if (lane == k) {
+        dinv[c0 + k] = il;
+        sg[c0 + k] = sgnk;
+        if (bad && state) atomicExch(&state[frame].info, c0 + k + 1);
+    }
+    if (i == k) myil = il;
+    const double v = e[k];
+    double u = v * sil, keep = (i > k) ? u : v * il;
+    if (i == k) {
+        u = sil;
+        keep = l;
+    }
+    e[k] = keep;
+    const double su = -sgnk * u;
+#pragma unroll
+    for (int c = k + 1; c < 16; ++c) {
+        const double uc = __shfl_sync(0xffffffffu, u, c);
+        if (i >= c || i <= k) e[c] = fma(su, uc, e[c]);
+    }
+    if constexpr (k + 1 < 16) pb_pivot<k + 1>(e, myil, i, lane, c0, dinv, sg, state, frame, pivot_tol);
+}
+
+constexpr int kPB = 16;
+constexpr int kPbLd = kTile + 1;
+constexpr int kPbSmem = (kTile * kPbLd + kPB * kTile + kPB * kPB + 2 * kTile) * (int)sizeof(double);
+
+__global__ void __launch_bounds__(kPotrfThreads)
+potrf_tile_blocked_kernel(double* A_, long lda, long strideA, double* Minv_, long strideM, double* sgn_,
+                          long strideSgn, int* neg_cnt_, int* neg_idx_, long strideNeg, ScfState* state,
+                          double pivot_tol) {
+    const int frame = blockIdx.z;
+    if (state && !state[frame].active) return;
+    extern __shared__ __align__(16) double psm[];
+    double* T = psm;                          // [128][129]
+    double* W = T + kTile * kPbLd;            // [16][128]
+    double* XD = W + kPB * kTile;             // [16][16]  X_D[j][m], zero above the diagonal
+    double* dinv = XD + kPB * kPB;            // [128]
+    double* sg = dinv + kTile;                // [128]
+    double* A = A_ + (long)frame * strideA;
+    double* Minv = Minv_ + (long)frame * strideM;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+
+    for (int idx = t; idx < kTile * kTile; idx += kPotrfThreads) {
+        const int r = idx & (kTile - 1), c = idx >> 7;
+        T[c * kPbLd + r] = (r >= c) ? A[r + (long)c * lda] : 0.0;
+    }
+    __syncthreads();
+
+    for (int K = 0; K < kTile / kPB; ++K) {
+        const int c0 = K * kPB;
+        // ---- A: diagonal block, warp 0 ----
+        if (warp == 0) {
+            const int i = lane & 15;
+            double e[kPB];
+#pragma unroll
+            for (int j = 0; j < kPB; ++j) e[j] = T[(c0 + j) * kPbLd + c0 + i];
+            double myil = 1.0;
+            pb_pivot<0>(e, myil, i, lane, c0, dinv, sg, state, frame, pivot_tol);
+            if (lane < kPB) {
+#pragma unroll
+                for (int j = 0; j < kPB; ++j) {
+                    T[(c0 + j) * kPbLd + c0 + i] = e[j];
+                    // X_D[j][i]: strict lower part from the transposed upper entries, diagonal 1 / l
+                    const double x = (i < j) ? e[j] : ((i == j) ? myil : 0.0);
+                    XD[j * kPB + i] = x;
+                    W[j * kTile + c0 + i] = x;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- B: all other rows through the block inverse ----
+        if (t < kTile && (t < c0 || t >= c0 + kPB)) {
+            const int r = t;
+            double v[kPB];
+#pragma unroll
+            for (int m = 0; m < kPB; ++m) v[m] = T[(c0 + m) * kPbLd + r];
+            const bool lrow = r >= c0 + kPB;
+#pragma unroll
+            for (int j = 0; j < kPB; ++j) {
+                double acc = 0.0;
+#pragma unroll
+                for (int m = 0; m <= j; ++m) acc = fma(v[m], XD[j * kPB + m], acc);
+                W[j * kTile + r] = acc;
+                T[(c0 + j) * kPbLd + r] = lrow ? sg[c0 + j] * acc : acc;
+            }
+        }
+        __syncthreads();
+        // ---- C: rank-16 update right of the block ----
+        if (c0 + kPB < kTile) {
+            const int xrows = c0 + kPB;               // rows below this bound are X rows (always updated)
+            double w[4][kPB];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int j = 0; j < kPB; ++j) w[a][j] = W[j * kTile + lane + 32 * a];
+            for (int c4 = xrows / 4 + warp; c4 < kTile / 4; c4 += kPotrfThreads / 32) {
+                const int cb = 4 * c4;
+#pragma unroll 1
+                for (int b = 0; b < 4; ++b) {
+                    const int c = cb + b;
+                    double lc[kPB];
+#pragma unroll
+                    for (int j = 0; j < kPB; ++j) lc[j] = T[(c0 + j) * kPbLd + c];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const int rlo = 32 * a;
+                        if (rlo >= xrows && rlo + 31 < c) continue;   // dead part of X (warp-uniform)
+                        const int r = rlo + lane;
+                        if (r >= c || r < xrows) {
+                            double acc = T[c * kPbLd + r];
+#pragma unroll
+                            for (int j = 0; j < kPB; ++j) acc = fma(-w[a][j], lc[j], acc);
+                            T[c * kPbLd + r] = acc;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // L back to global (lower part); M = S X with M[i][j] = s_i X[i][j] (i > j), s_i / l_i on the diagonal
+    for (int idx = t; idx < kTile * kTile; idx += kPotrfThreads) {
+        const int i = idx & (kTile - 1), j = idx >> 7;
+        if (i >= j) A[i + (long)j * lda] = T[j * kPbLd + i];
+        double m = 0.0;
+        if (i > j) m = sg[i] * T[i * kPbLd + j];
+        else if (i == j) m = sg[i] * dinv[i];
+        Minv[idx] = m;
+    }
+    if (t < kTile && sgn_) sgn_[(long)frame * strideSgn + t] = sg[t];
+    if (t == 0 && neg_cnt_) {
+        int n = 0;
+        int* idx = neg_idx_ + (long)frame * strideNeg * kTile;
+        for (int i = 0; i < kTile; ++i)
+            if (sg[i] < 0.0) idx[n++] = i;
+        neg_cnt_[(long)frame * strideNeg] = n;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 copy_lower_tiles_kernel(const double* src, long lds, long stride_src, double* dst, long ldd, long stride_dst,
                         const ScfState* state, const uint8_t* col_mask) {
@@ -899,18 +1067,28 @@ cudaError_t launch_potrf_tile(double* A, long lda, long strideA, double* Linv, l
     // 2x SLOWER than the rank-1 DFMA kernel (132 vs 66 us per tile) because ptxas keeps part of the 128-register
     // tile in local memory (512 B stack frame), so the DFMA kernel stays the default.
     static bool use_scalar = true;
+    static bool use_rank1 = false;   // CHEQ_POTRF_RANK1=1: the register-resident rank-1 kernel (previous default)
     if (!configured) {
         cudaError_t e =
             cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPotrfSmem);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(potrf_tile_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPotrfSmem);
         if (e != cudaSuccess) return e;
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(potrf_tile_blocked_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPbSmem);
+        if (e != cudaSuccess) return e;
         const char* env = getenv("CHEQ_POTRF_DMMA");
         use_scalar = !(env && env[0] == '1');
+        const char* env1 = getenv("CHEQ_POTRF_RANK1");
+        use_rank1 = env1 && env1[0] == '1';
         configured = true;
     }
     dim3 grid(1, 1, batch);
-    if (use_scalar)
+    if (use_scalar && !use_rank1)
+        potrf_tile_blocked_kernel<<<grid, kPotrfThreads, kPbSmem, stream>>>(A, lda, strideA, Linv, strideLinv, sgn,
+                                                                               strideSgn, neg_cnt, neg_idx, strideNeg,
+                                                                               state, pivot_tol);
+    else if (use_scalar)
         potrf_tile_kernel<<<grid, kPotrfThreads, kPotrfSmem, stream>>>(A, lda, strideA, Linv, strideLinv, sgn, strideSgn,
                                                                        neg_cnt, neg_idx, strideNeg, state, pivot_tol);
     else
