@@ -62,6 +62,7 @@ SIGNATURES = {
     "cheq_external_potential": (_I32, [_P, _U64, _P, _P, _P, C.POINTER(External), _D, _U8, _P]),
     "cheq_dbg_cholesky_solve": (_I32, [_P, _U64, _P, _U64, _P, _P, _P]),
     "cheq_dbg_gemm_nt": (_I32, [_P, _U64, _U64, _U64, _P, _P, _P, _I32]),
+    "cheq_dbg_potrf_cycles": (_I32, [_P, _P, _I32]),
     "cheq_dbg_dfma_rate": (_I32, [_P, C.POINTER(_D)]),
     "cheq_dbg_gemm_bench": (_I32, [_P, _U64, _U64, _U64, _I32, _I32, _I32, C.POINTER(_D)]),
     "cheq_host_sto_table_eval": (_D, [_I32, _D, _I32, _D, _D, C.POINTER(_I32), C.POINTER(_I32), C.POINTER(_I32),

@@ -1889,6 +1889,15 @@ int32_t cheq_dbg_gemm_bench(cheq_ctx* ctx, uint64_t m, uint64_t n, uint64_t k, i
     return CHEQ_OK;
 }
 
+int32_t cheq_dbg_potrf_cycles(cheq_ctx* ctx, uint64_t* out8, int32_t reset) {
+    if (!ctx || !out8) return CHEQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(potrf_debug_cycles((unsigned long long*)out8, reset));
+    return CHEQ_OK;
+}
+
 int32_t cheq_dbg_dfma_rate(cheq_ctx* ctx, double* tflops_out) {
     if (!ctx || !tflops_out) return CHEQ_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(ctx->mu);
@@ -1916,6 +1925,19 @@ int32_t cheq_dbg_dfma_rate(cheq_ctx* ctx, double* tflops_out) {
         cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
         const double tf = 512.0 * 16.0 * it2 * (double)b2 * (threads / 32) / (ms * 1e-3) / 1e12;
         report += "dmma " + std::to_string(threads / 128) + " warps/SMSP: " + std::to_string(tf) + " TF/s; ";
+    }
+    {
+        const int iters = 4096;
+        long long* d_cyc = (long long*)(ctx->misc0.as<double>() + 64);
+        LAUNCH(launch_latency_probe(ctx->misc0.as<double>(), d_cyc, iters, ctx->stream));
+        long long h[5];
+        CU(cudaMemcpyAsync(h, d_cyc, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        char buf[256];
+        snprintf(buf, sizeof buf, "latency cycles: dfma %.1f shfl64 %.1f dmma %.1f lds+dadd %.1f rsqrtf+fadd %.1f",
+                 (double)h[0] / iters, (double)h[1] / iters, (double)h[2] / iters, (double)h[3] / iters,
+                 (double)h[4] / iters);
+        report += buf;
     }
     ctx->err = report;
     return CHEQ_OK;

@@ -82,6 +82,7 @@ cudaError_t launch_export_matrix(int NP, long ld, const double* A, const int* pe
 // ---- dense (kernels_dense.cu) ------------------------------------------------------------------------------
 cudaError_t launch_gemm_nt(const GemmArgs& g, int m_tiles, int n_tiles, int batch, cudaStream_t stream);
 cudaError_t launch_dmma_rate(double* out, int blocks, int threads, int iters, cudaStream_t stream);
+cudaError_t launch_latency_probe(double* out, long long* cycles, int iters, cudaStream_t stream);
 cudaError_t launch_dfma_rate(double* out, int blocks, int iters, cudaStream_t stream);
 void set_gemm_warps(int warps);   // tuning knob: 8 or 16 warps per GEMM CTA
 // A = L S L^T of one 128 x 128 diagonal block in place (lower) + M = S L^-1 (dense 128 x 128, ld 128) + the signs.
@@ -108,6 +109,8 @@ cudaError_t launch_backsolve_step(const double* A, long lda, long strideA, const
                                   const double* sgn, long strideSgn, int NP, int kb, double* v, double* x,
                                   long v_stride, const ScfState* state, int batch, cudaStream_t stream);
 int backsolve_max_ctas();
+// debug: accumulated cycle counters of the blocked diagonal-tile kernel {load, A, B, C, store, launches, -, -}
+cudaError_t potrf_debug_cycles(unsigned long long* out, int reset);
 // delta = max |x - q| over real atoms; q <- (1 - d) q + d x
 cudaError_t launch_scf_mix(const double* x, double* q, long stride, const uint8_t* type, int NP, ScfState* state,
                            int batch, cudaStream_t stream);

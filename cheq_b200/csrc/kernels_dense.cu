@@ -609,7 +609,7 @@ potrf_tile_dmma_kernel(double* A_, long lda, long strideA, double* Minv_, long s
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Diagonal tile, shared-memory blocked variant (default).  Same outputs as potrf_tile_kernel.
+// Diagonal tile, shared-memory blocked variant (experimental, CHEQ_POTRF_BLOCKED=1).  Same outputs as potrf_tile_kernel.
 //
 // The 128 x 128 tile lives in shared memory, T[c * 129 + r]; as in the rank-1 kernel the lower part (r >= c)
 // becomes L and the strict upper part (r < c) holds X[c][r], X = L^-1 (forward elimination of the identity).
@@ -659,6 +659,8 @@ __device__ __forceinline__ void pb_pivot(double (&e)[16], double& myil, int i, i
 }
 
 constexpr int kPB = 16;
+// cycle counters of the blocked diagonal-tile kernel (thread 0 of the CTA): load, phase A, B, C, store, launches
+__device__ unsigned long long g_potrf_cycles[8];
 constexpr int kPbLd = kTile + 1;
 constexpr int kPbSmem = (kTile * kPbLd + kPB * kTile + kPB * kPB + 2 * kTile) * (int)sizeof(double);
 
@@ -677,15 +679,18 @@ potrf_tile_blocked_kernel(double* A_, long lda, long strideA, double* Minv_, lon
     double* A = A_ + (long)frame * strideA;
     double* Minv = Minv_ + (long)frame * strideM;
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    long long tk0 = clock64(), tkA = 0, tkB = 0, tkC = 0;
 
     for (int idx = t; idx < kTile * kTile; idx += kPotrfThreads) {
         const int r = idx & (kTile - 1), c = idx >> 7;
         T[c * kPbLd + r] = (r >= c) ? A[r + (long)c * lda] : 0.0;
     }
     __syncthreads();
+    const long long tkLoad = clock64() - tk0;
 
     for (int K = 0; K < kTile / kPB; ++K) {
         const int c0 = K * kPB;
+        long long tk1 = clock64();
         // ---- A: diagonal block, warp 0 ----
         if (warp == 0) {
             const int i = lane & 15;
@@ -706,6 +711,8 @@ potrf_tile_blocked_kernel(double* A_, long lda, long strideA, double* Minv_, lon
             }
         }
         __syncthreads();
+        tkA += clock64() - tk1;
+        tk1 = clock64();
         // ---- B: all other rows through the block inverse ----
         if (t < kTile && (t < c0 || t >= c0 + kPB)) {
             const int r = t;
@@ -723,6 +730,8 @@ potrf_tile_blocked_kernel(double* A_, long lda, long strideA, double* Minv_, lon
             }
         }
         __syncthreads();
+        tkB += clock64() - tk1;
+        tk1 = clock64();
         // ---- C: rank-16 update right of the block ----
         if (c0 + kPB < kTile) {
             const int xrows = c0 + kPB;               // rows below this bound are X rows (always updated)
@@ -755,7 +764,9 @@ potrf_tile_blocked_kernel(double* A_, long lda, long strideA, double* Minv_, lon
             }
         }
         __syncthreads();
+        tkC += clock64() - tk1;
     }
+    const long long tkS0 = clock64();
 
     // L back to global (lower part); M = S X with M[i][j] = s_i X[i][j] (i > j), s_i / l_i on the diagonal
     for (int idx = t; idx < kTile * kTile; idx += kPotrfThreads) {
@@ -773,6 +784,14 @@ potrf_tile_blocked_kernel(double* A_, long lda, long strideA, double* Minv_, lon
         for (int i = 0; i < kTile; ++i)
             if (sg[i] < 0.0) idx[n++] = i;
         neg_cnt_[(long)frame * strideNeg] = n;
+    }
+    if (t == 0) {
+        atomicAdd(&g_potrf_cycles[0], (unsigned long long)tkLoad);
+        atomicAdd(&g_potrf_cycles[1], (unsigned long long)tkA);
+        atomicAdd(&g_potrf_cycles[2], (unsigned long long)tkB);
+        atomicAdd(&g_potrf_cycles[3], (unsigned long long)tkC);
+        atomicAdd(&g_potrf_cycles[4], (unsigned long long)(clock64() - tkS0));
+        atomicAdd(&g_potrf_cycles[5], 1ull);
     }
 }
 
@@ -1009,6 +1028,48 @@ __global__ void dmma_rate_kernel(double* out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+// Dependent-issue latencies (one warp, one chain): DFMA, shuffle of a double, DMMA, shared-memory load
+__global__ void latency_probe_kernel(double* out, long long* cycles, int iters) {
+    __shared__ double sm[64];
+    sm[threadIdx.x] = 1.0 + threadIdx.x * 1e-9;
+    sm[threadIdx.x + 32] = 0.5;
+    __syncthreads();
+    double a = 1.0 + threadIdx.x * 1e-9;
+    const double x = 1.0000001, y = 1e-9;
+    long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) a = fma(a, x, y);
+    long long t1 = clock64();
+    double b = a;
+    for (int i = 0; i < iters; ++i) b = __shfl_sync(0xffffffffu, b, (threadIdx.x + 1) & 31);
+    long long t2 = clock64();
+    double c0 = b, c1 = a;
+    for (int i = 0; i < iters; ++i) dmma884(c0, c1, c0, x);
+    long long t3 = clock64();
+    int idx = threadIdx.x;
+    double d = c0;
+    for (int i = 0; i < iters; ++i) {
+        d += sm[idx];
+        idx = (idx + (int)(d > 1e300)) & 31;   // address depends on the loaded value
+    }
+    long long t4 = clock64();
+    float f = (float)d;
+    for (int i = 0; i < iters; ++i) f = rsqrtf(f) + 1.0f;
+    long long t5 = clock64();
+    out[threadIdx.x] = a + b + c0 + c1 + d + f;
+    if (threadIdx.x == 0) {
+        cycles[0] = t1 - t0;
+        cycles[1] = t2 - t1;
+        cycles[2] = t3 - t2;
+        cycles[3] = t4 - t3;
+        cycles[4] = t5 - t4;
+    }
+}
+
+cudaError_t launch_latency_probe(double* out, long long* cycles, int iters, cudaStream_t stream) {
+    latency_probe_kernel<<<1, 32, 0, stream>>>(out, cycles, iters);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_dmma_rate(double* out, int blocks, int threads, int iters, cudaStream_t stream) {
     dmma_rate_kernel<<<blocks, threads, 0, stream>>>(out, iters);
     return cudaGetLastError();
@@ -1017,6 +1078,15 @@ cudaError_t launch_dmma_rate(double* out, int blocks, int threads, int iters, cu
 cudaError_t launch_dfma_rate(double* out, int blocks, int iters, cudaStream_t stream) {
     dfma_rate_kernel<<<blocks, 256, 0, stream>>>(out, iters);
     return cudaGetLastError();
+}
+
+cudaError_t potrf_debug_cycles(unsigned long long* out, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_potrf_cycles, sizeof(g_potrf_cycles));
+    if (e == cudaSuccess && reset) {
+        unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        e = cudaMemcpyToSymbol(g_potrf_cycles, z, sizeof(z));
+    }
+    return e;
 }
 
 int g_gemm_warps = 16;        // warps per 128 x 128 GEMM CTA: 8 (64 x 32 warp tiles) or 16 (32 x 32)
@@ -1067,7 +1137,10 @@ cudaError_t launch_potrf_tile(double* A, long lda, long strideA, double* Linv, l
     // 2x SLOWER than the rank-1 DFMA kernel (132 vs 66 us per tile) because ptxas keeps part of the 128-register
     // tile in local memory (512 B stack frame), so the DFMA kernel stays the default.
     static bool use_scalar = true;
-    static bool use_rank1 = false;   // CHEQ_POTRF_RANK1=1: the register-resident rank-1 kernel (previous default)
+    // CHEQ_POTRF_BLOCKED=1: the shared-memory blocked kernel (measured 86 us per tile vs 66 us: in-kernel clock64
+    // counters show 68k cycles in the 16 x 16 diagonal blocks, 20k in the block-inverse pass, 60k in the rank-16
+    // updates -- shared-memory bound; profiles/r1_potrf_variants.txt)
+    static bool use_rank1 = true;
     if (!configured) {
         cudaError_t e =
             cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPotrfSmem);
@@ -1079,8 +1152,8 @@ cudaError_t launch_potrf_tile(double* A, long lda, long strideA, double* Linv, l
         if (e != cudaSuccess) return e;
         const char* env = getenv("CHEQ_POTRF_DMMA");
         use_scalar = !(env && env[0] == '1');
-        const char* env1 = getenv("CHEQ_POTRF_RANK1");
-        use_rank1 = env1 && env1[0] == '1';
+        const char* env1 = getenv("CHEQ_POTRF_BLOCKED");
+        use_rank1 = !(env1 && env1[0] == '1');
         configured = true;
     }
     dim3 grid(1, 1, batch);

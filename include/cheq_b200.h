@@ -192,6 +192,11 @@ int32_t cheq_dbg_gemm_nt(cheq_ctx* ctx, uint64_t m, uint64_t n, uint64_t k, cons
 int32_t cheq_dbg_gemm_bench(cheq_ctx* ctx, uint64_t m, uint64_t n, uint64_t k, int32_t lower, int32_t subtract,
                             int32_t reps, double* ms_out);
 
+/* Debug: SM-cycle counters of the diagonal-tile factorisation kernel accumulated since the last reset:
+ * {load, phase A (diagonal 16 x 16 blocks), phase B (block inverse applied), phase C (rank-16 updates), store,
+ * launches, 0, 0}. */
+int32_t cheq_dbg_potrf_cycles(cheq_ctx* ctx, uint64_t* out8, int32_t reset);
+
 /* Plain FP64 FMA (non-tensor) throughput of the device in TFLOP/s: the ALU roofline of the STO assembly. */
 int32_t cheq_dbg_dfma_rate(cheq_ctx* ctx, double* tflops_out);
 
