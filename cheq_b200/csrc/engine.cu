@@ -210,7 +210,7 @@ struct cheq_ctx {
     int factor_mode = 0;                   // 0: auto (recursive on one GPU, blocked when world > 1), 1: blocked
     int tiles_per_panel = 4;
     PanelPlan pplan;
-    DeviceBuffer stage, own_list, col_mask;
+    DeviceBuffer stage, own_list, col_mask, chain;
     double ms_comm_host = 0.0;
     std::mutex mu;
     std::string err;
@@ -654,6 +654,13 @@ int schur_update(Dense& D, int k, int ncols) {
 int backsolve(Dense& D, int NP, double* v, double* x, long v_stride) {
     cheq_ctx* ctx = D.ctx;
     if (int rcp = prof_begin(ctx, 2)) return rcp;
+    static const bool steps = [] { const char* e = getenv("CHEQ_BACKSOLVE_STEPS"); return e && e[0] == '1'; }();
+    if (!steps) {
+        CU(ctx->chain.ensure((size_t)D.batch * (NP / kTile + 1) * sizeof(unsigned)));
+        LAUNCH(launch_backsolve_chain(D.A, D.ld, D.strideA, D.Linv, D.strideLinv, D.sgn, D.strideSgn, NP, v, x,
+                                      v_stride, ctx->chain.as<unsigned>(), D.state, D.batch, ctx->cur));
+        return prof_end(ctx);
+    }
     for (int kb = NP / kTile - 1; kb >= 0; --kb)
         LAUNCH(launch_backsolve_step(D.A, D.ld, D.strideA, D.Linv, D.strideLinv, D.sgn, D.strideSgn, NP, kb, v, x,
                                      v_stride, D.state, D.batch, ctx->cur));
@@ -1457,6 +1464,7 @@ void cheq_ctx_destroy(cheq_ctx* ctx) {
     ctx->stage.release();
     ctx->own_list.release();
     ctx->col_mask.release();
+    ctx->chain.release();
     if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
     if (ctx->ev_bcast) cudaEventDestroy(ctx->ev_bcast);
     if (ctx->panel_stream) cudaStreamDestroy(ctx->panel_stream);

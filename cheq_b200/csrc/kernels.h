@@ -109,6 +109,12 @@ cudaError_t launch_backsolve_step(const double* A, long lda, long strideA, const
                                   const double* sgn, long strideSgn, int NP, int kb, double* v, double* x,
                                   long v_stride, const ScfState* state, int batch, cudaStream_t stream);
 int backsolve_max_ctas();
+// the whole backward substitution as one kernel (chain of CTAs linked by flags); work: batch * (NP / 128 + 1)
+// unsigned (tickets + flags, cleared by the launcher); v is not modified
+cudaError_t launch_backsolve_chain(const double* A, long lda, long strideA, const double* Linv, long strideLinv,
+                                   const double* sgn, long strideSgn, int NP, const double* v, double* x,
+                                   long v_stride, unsigned* work, const ScfState* state, int batch,
+                                   cudaStream_t stream);
 // debug: accumulated cycle counters of the blocked diagonal-tile kernel {load, A, B, C, store, launches, -, -}
 cudaError_t potrf_debug_cycles(unsigned long long* out, int reset);
 // delta = max |x - q| over real atoms; q <- (1 - d) q + d x

@@ -228,6 +228,20 @@ __global__ void __launch_bounds__(WM * 4 * 32, 1) gemm_nt_kernel(GemmArgs g) {
 // one half-warp, which gets the pivot by shuffle -- and publishes it as u[0..127]; then every element with c > k
 // and (r >= c or r <= k) takes  e -= s u[r] u[c].  One __syncthreads per step (u is double buffered).
 // ------------------------------------------------------------------------------------------------------------
+// 1/sqrt(x) for x in the range of pivots (1e-30 .. 1e30): single-precision seed + two Newton steps in fp64
+// (23 -> 46 -> 53+ bits).  No library call: the CUDA rsqrt() keeps a slow-path subroutine that forces the
+// register-resident tile through a stack frame.
+__device__ __forceinline__ double rsqrt_pivot(double x) {
+    double y = (double)rsqrtf((float)x);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const double t = x * y;
+        const double h = fma(-t, y, 1.0);
+        y = fma(0.5 * y, h, y);
+    }
+    return y;
+}
+
 constexpr int kPotrfThreads = 256;
 constexpr int kPotrfLd = kTile + 1;
 constexpr int kPotrfSmem = kTile * kPotrfLd * (int)sizeof(double);
@@ -265,10 +279,10 @@ potrf_tile_kernel(double* A_, long lda, long strideA, double* Minv_, long stride
             const double d = __shfl_sync(0xffffffffu, e[kb][kb], kt + 16 * (tx & 1));
             if (tx == kt) {
                 const double ad = fabs(d);
-                const bool bad = !(ad > pivot_tol) || !(ad < 1.0e300);
+                const bool bad = !(ad > pivot_tol) || !(ad < 1.0e30);
                 const double sgnk = (d < 0.0) ? -1.0 : 1.0;
                 // 1/sqrt and sqrt from one rsqrt plus a Newton step (shorter dependent chain than sqrt + divide)
-                double il = bad ? 1.0 : rsqrt(ad);
+                double il = bad ? 1.0 : rsqrt_pivot(ad);
                 double l = bad ? 1.0 : ad * il;
                 if (!bad) {
                     const double res = fma(-l, l, ad);        // ad - l^2
@@ -375,20 +389,6 @@ potrf_tile_kernel(double* A_, long lda, long strideA, double* Minv_, long stride
 // (r >= c or r <= k).
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void dmma884_acc(double (&c)[2], double a, double b) { dmma884(c[0], c[1], a, b); }
-
-// 1/sqrt(x) for x in the range of pivots (1e-30 .. 1e30): single-precision seed + two Newton steps in fp64
-// (23 -> 46 -> 53+ bits).  No library call: the CUDA rsqrt() keeps a slow-path subroutine that forces the
-// register-resident tile through a stack frame.
-__device__ __forceinline__ double rsqrt_pivot(double x) {
-    double y = (double)rsqrtf((float)x);
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const double t = x * y;
-        const double h = fma(-t, y, 1.0);
-        y = fma(0.5 * y, h, y);
-    }
-    return y;
-}
 
 template <int TCB, int HALF>
 __device__ __forceinline__ void potrf3_step(double (&c)[2][16][2], int warp, int lane, double (*Pn)[kTile],
@@ -929,6 +929,125 @@ backsolve_step_kernel(const double* A_, long lda, long strideA, const double* Mi
     }
 }
 
+// Backward substitution L^T x = v as ONE kernel: a chain of CTAs linked by release/acquire flags in global memory.
+// CTA b (one per 128-column block; blocks are claimed by ticket from the last to the first) owns v_b privately:
+//   for kb = last .. b + 1 (as soon as x_kb is published):  acc_b += L[kb rows, b cols]^T x_kb   (HBM stream,
+//     128 KB per tile, per-lane partial sums: no cross-lane reduction inside the loop)
+//   then v_b -= reduce(acc_b);  x_b = M_b^T (S v_b)  with M_b = S L_bb^-1 staged in shared memory at kernel start;
+//   publish x_b, __threadfence, flag[b] = epoch.
+// Only the CTA right below the chain head is latency-critical (one tile + one triangular product per link,
+// ~2-3 us); all others stream their tiles at HBM speed behind it.  A CTA waits only on CTAs with a smaller
+// ticket (tickets are handed out as CTAs start), so the chain cannot deadlock even when the grid exceeds the
+// number of resident CTAs.  Fixed summation order: results are bit-reproducible (the replicated solves of all ranks agree).
+constexpr int kChainPacked = kTile * (kTile + 1) / 2;                 // lower triangle of M_b, packed by row
+constexpr int kChainRedLd = 17;
+constexpr int kChainSmem = (kChainPacked + 8 * 32 * kChainRedLd + 4 * kTile) * (int)sizeof(double);
+
+__global__ void __launch_bounds__(256, 2)
+backsolve_chain_kernel(const double* A_, long lda, long strideA, const double* Minv_, long strideM,
+                       const double* sgn_, long strideSgn, int nb, const double* v_, double* x_, long v_stride,
+                       unsigned* flags_, unsigned* tickets, const ScfState* state) {
+    const int frame = blockIdx.z;
+    if (state && !state[frame].active) return;
+    // block index by ticket: the order in which CTAs start IS the order of the chain (no assumption about the
+    // hardware's dispatch order)
+    __shared__ int b_s;
+    if (threadIdx.x == 0) b_s = nb - 1 - (int)atomicAdd(&tickets[frame], 1u);
+    __syncthreads();
+    const int b = b_s;
+    const unsigned epoch = 1u;
+    extern __shared__ __align__(16) double csm[];
+    double* Mp = csm;                                  // Mp[j (j + 1) / 2 + i] = M[j][i], i <= j
+    double* red = Mp + kChainPacked;                   // [8 warps][32 lanes][17]
+    double* tv = red + 8 * 32 * kChainRedLd;           // [128] S v_b
+    double* xs = tv + kTile;                           // [128] x_kb of the tile being applied / x_b
+    double* part = xs + kTile;                         // [2][128]
+    __shared__ int ready_s;
+    const double* A = A_ + (long)frame * strideA;
+    const double* Minv = Minv_ + (long)frame * strideM + (long)b * kTile * kTile;
+    const double* sgn = sgn_ + (long)frame * strideSgn + b * kTile;
+    const double* v = v_ + (long)frame * v_stride;
+    double* x = x_ + (long)frame * v_stride;
+    volatile unsigned* flags = flags_ + (long)frame * nb;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+
+    // stage M_b (lower triangle) while the blocks above are still being solved
+    for (int idx = t; idx < kTile * kTile; idx += 256) {
+        const int j = idx & (kTile - 1), i = idx >> 7;   // row j, column i of M (column-major in global memory)
+        if (j >= i) Mp[j * (j + 1) / 2 + i] = Minv[idx];
+    }
+
+    // per-lane partial sums of the 16 columns of this warp: column b 128 + 16 warp + c, rows lane + 32 m
+    double acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = 0.0;
+    const double* Lcol = A + ((long)b * kTile + 16 * warp) * lda + lane;
+    int kb = nb - 1;
+    while (kb > b) {
+        // how many of the next (up to 32) blocks are already published?
+        if (warp == 0) {
+            const int k = kb - lane;
+            unsigned ok = 0;
+            do {
+                const bool mine_ready = (k > b) ? (flags[k] == epoch) : true;
+                ok = __ballot_sync(0xffffffffu, mine_ready);
+            } while ((ok & 1u) == 0u);                   // at least block kb must be there
+            const int run = __ffs(~ok) - 1;              // consecutive ready blocks from kb downwards (32 if all)
+            if (lane == 0) ready_s = (run < 0) ? 32 : run;
+        }
+        __syncthreads();
+        __threadfence();                                 // acquire: x of the published blocks is visible
+        int nready = ready_s;
+        if (nready > kb - b) nready = kb - b;
+        for (int q = 0; q < nready; ++q, --kb) {
+            const double* xk = x + (long)kb * kTile;
+            const double x0 = __ldcg(xk + lane), x1 = __ldcg(xk + lane + 32), x2 = __ldcg(xk + lane + 64),
+                         x3 = __ldcg(xk + lane + 96);
+            const double* Lt = Lcol + (long)kb * kTile;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const double* p = Lt + (long)c * lda;
+                const double l0 = __ldcs(p), l1 = __ldcs(p + 32), l2 = __ldcs(p + 64), l3 = __ldcs(p + 96);
+                acc[c] = fma(l0, x0, acc[c]);
+                acc[c] = fma(l1, x1, acc[c]);
+                acc[c] = fma(l2, x2, acc[c]);
+                acc[c] = fma(l3, x3, acc[c]);
+            }
+        }
+        __syncthreads();                                 // ready_s is rewritten in the next round
+    }
+    // reduce the per-lane partials: red[warp][lane][c]
+#pragma unroll
+    for (int c = 0; c < 16; ++c) red[(warp * 32 + lane) * kChainRedLd + c] = acc[c];
+    __syncthreads();
+    if (t < kTile) {
+        const int w = t >> 4, c = t & 15;
+        double s = 0.0;
+#pragma unroll 8
+        for (int l = 0; l < 32; ++l) s += red[(w * 32 + l) * kChainRedLd + c];
+        tv[t] = sgn[t] * (v[b * kTile + t] - s);
+    }
+    __syncthreads();
+    {   // x_i = sum_{j >= i} M[j][i] (S v)_j : thread (i, h) takes the rows j of parity h
+        const int i = t & (kTile - 1), h = t >> 7;
+        double s = 0.0;
+        int j = i + ((i + h) & 1);                       // first row >= i with j % 2 == h
+        for (; j < kTile; j += 2) s = fma(Mp[j * (j + 1) / 2 + i], tv[j], s);
+        part[h * kTile + i] = s;
+    }
+    __syncthreads();
+    if (t < kTile) {
+        const double xi = part[t] + part[kTile + t];
+        __stcg(x + (long)b * kTile + t, xi);
+        __threadfence();
+    }
+    __syncthreads();
+    if (t == 0) {
+        __threadfence();
+        flags[b] = epoch;
+    }
+}
+
 __global__ void __launch_bounds__(256)
 scf_mix_kernel(const double* x_, double* q_, long stride, const uint8_t* type, int NP, ScfState* state) {
     const int frame = blockIdx.z;
@@ -1199,6 +1318,27 @@ cudaError_t launch_mu(const double* A, long lda, long strideA, int NP, double to
 }
 
 int backsolve_max_ctas() { return 1; }
+
+cudaError_t launch_backsolve_chain(const double* A, long lda, long strideA, const double* Linv, long strideLinv,
+                                   const double* sgn, long strideSgn, int NP, const double* v, double* x,
+                                   long v_stride, unsigned* work, const ScfState* state, int batch,
+                                   cudaStream_t stream) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(backsolve_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             kChainSmem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int nb = NP / kTile;
+    // work = [batch] tickets, then [batch][nb] flags
+    cudaError_t e = cudaMemsetAsync(work, 0, (size_t)batch * (nb + 1) * sizeof(unsigned), stream);
+    if (e != cudaSuccess) return e;
+    dim3 grid(nb, 1, batch);
+    backsolve_chain_kernel<<<grid, 256, kChainSmem, stream>>>(A, lda, strideA, Linv, strideLinv, sgn, strideSgn, nb,
+                                                              v, x, v_stride, work + batch, work, state);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_backsolve_step(const double* A, long lda, long strideA, const double* Linv, long strideLinv,
                                   const double* sgn, long strideSgn, int NP, int kb, double* v, double* x,
