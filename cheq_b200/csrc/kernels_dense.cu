@@ -228,20 +228,21 @@ __global__ void __launch_bounds__(WM * 4 * 32, 1) gemm_nt_kernel(GemmArgs g) {
 // one half-warp, which gets the pivot by shuffle -- and publishes it as u[0..127]; then every element with c > k
 // and (r >= c or r <= k) takes  e -= s u[r] u[c].  One __syncthreads per step (u is double buffered).
 // ------------------------------------------------------------------------------------------------------------
-// 1/sqrt(x) for x in the range of pivots (1e-30 .. 1e30): single-precision seed + two Newton steps in fp64
-// (23 -> 46 -> 53+ bits).  No library call: the CUDA rsqrt() keeps a slow-path subroutine that forces the
-// register-resident tile through a stack frame.
+// 1/sqrt(x) for x in the range of pivots (1e-4 .. 1e30): the hardware's double-precision seed
+// (rsqrt.approx.ftz.f64 = MUFU.RSQ64H on the high word, ~2^-20 relative) plus ONE Newton step (-> ~2^-40); the
+// callers' joint correction of l = x * y and y brings both to full precision.  No f64 <-> f32 conversions, no
+// library slow path, no branches: this sits on the per-pivot dependency chain of the diagonal-tile kernels.
 __device__ __forceinline__ double rsqrt_pivot(double x) {
-    double y = (double)rsqrtf((float)x);
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const double t = x * y;
-        const double h = fma(-t, y, 1.0);
-        y = fma(0.5 * y, h, y);
-    }
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double t = x * y;
+    const double h = fma(-t, y, 1.0);
+    y = fma(0.5 * y, h, y);
     return y;
 }
 
+// debug cycle counters of the diagonal-tile kernels (see cheq_dbg_potrf_cycles)
+__device__ unsigned long long g_potrf_cycles[8];
 constexpr int kPotrfThreads = 256;
 constexpr int kPotrfLd = kTile + 1;
 constexpr int kPotrfSmem = kTile * kPotrfLd * (int)sizeof(double);
@@ -271,10 +272,17 @@ potrf_tile_kernel(double* A_, long lda, long strideA, double* Minv_, long stride
 
     const bool p_diag = ty >= tx;   // within a diagonal 16 x 16 sub-block: element on or below the diagonal
     int cur = 0;
+#ifdef CHEQ_POTRF_INSTRUMENT
+#define POTRF_CLOCK() clock64()
+#else
+#define POTRF_CLOCK() 0ll
+#endif
+    long long tkChain = 0, tkBar = 0, tkUpd = 0, tkAll0 = POTRF_CLOCK();
 #pragma unroll
     for (int kb = 0; kb < 8; ++kb) {
         for (int kt = 0; kt < 16; ++kt) {
             const int k = kb * 16 + kt;
+            const long long tc0 = POTRF_CLOCK();
             // pivot: element (k, k) lives in thread (ty = kt, tx = kt), register e[kb][kb]
             const double d = __shfl_sync(0xffffffffu, e[kb][kb], kt + 16 * (tx & 1));
             if (tx == kt) {
@@ -282,13 +290,15 @@ potrf_tile_kernel(double* A_, long lda, long strideA, double* Minv_, long stride
                 const bool bad = !(ad > pivot_tol) || !(ad < 1.0e30);
                 const double sgnk = (d < 0.0) ? -1.0 : 1.0;
                 // 1/sqrt and sqrt from one rsqrt plus a Newton step (shorter dependent chain than sqrt + divide)
-                double il = bad ? 1.0 : rsqrt_pivot(ad);
-                double l = bad ? 1.0 : ad * il;
-                if (!bad) {
+                double il = rsqrt_pivot(ad);
+                double l = ad * il;
+                {
                     const double res = fma(-l, l, ad);        // ad - l^2
                     l = fma(0.5 * il, res, l);
                     il = fma(fma(-l, il, 1.0), il, il);
                 }
+                il = bad ? 1.0 : il;
+                l = bad ? 1.0 : l;
                 const double sil = sgnk * il;
                 if (ty == kt) {
                     dinv[k] = il;
@@ -314,7 +324,9 @@ potrf_tile_kernel(double* A_, long lda, long strideA, double* Minv_, long stride
                     ubuf[cur][ty + 16 * a] = u;
                 }
             }
+            const long long tc1 = POTRF_CLOCK();
             __syncthreads();
+            const long long tc2 = POTRF_CLOCK();
             const double sk = sg[k];
             const bool p_row = ty <= kt;    // rows of block kb that are <= k
             const bool p_col = tx > kt;     // columns of block kb that are > k
@@ -341,9 +353,27 @@ potrf_tile_kernel(double* A_, long lda, long strideA, double* Minv_, long stride
                 }
             }
             cur ^= 1;
+            if (tx == kt && ty == kt) {   // the pivot thread: chain, barrier wait and update time of this step
+                tkChain += tc1 - tc0;
+                tkBar += tc2 - tc1;
+                tkUpd += POTRF_CLOCK() - tc2;
+            }
         }
     }
     __syncthreads();
+#ifdef CHEQ_POTRF_INSTRUMENT
+    if (tkChain) {
+        atomicAdd(&g_potrf_cycles[1], (unsigned long long)tkChain);
+        atomicAdd(&g_potrf_cycles[2], (unsigned long long)tkBar);
+        atomicAdd(&g_potrf_cycles[3], (unsigned long long)tkUpd);
+    }
+    if (t == 0) {
+        atomicAdd(&g_potrf_cycles[0], (unsigned long long)(clock64() - tkAll0));
+        atomicAdd(&g_potrf_cycles[5], 1ull);
+    }
+#else
+    (void)tkChain; (void)tkBar; (void)tkUpd; (void)tkAll0;
+#endif
 
     // L back to global; M = S X staged through shared memory (M[i][j] = s_i X[i][j], i > j, held as element (j, i))
 #pragma unroll
@@ -354,6 +384,172 @@ potrf_tile_kernel(double* A_, long lda, long strideA, double* Minv_, long stride
             if (r >= c) A[r + (long)c * lda] = e[a][b];
             // Ms[j * ld + i] = M[i][j]; the holder of (r, c) fills M[c][r]: X part below the diagonal of M,
             // the diagonal, and zeros above it
+            double m = 0.0;
+            if (r < c) m = sg[c] * e[a][b];
+            else if (r == c) m = sg[r] * dinv[r];
+            Ms[r * kPotrfLd + c] = m;
+        }
+    __syncthreads();
+    for (int idx = t; idx < kTile * kTile; idx += kPotrfThreads) {
+        const int i = idx & (kTile - 1), j = idx >> 7;
+        Minv[idx] = Ms[j * kPotrfLd + i];
+    }
+    if (t < kTile && sgn_) sgn_[(long)frame * strideSgn + t] = sg[t];
+    if (t == 0 && neg_cnt_) {   // compact list of this tile's negative pivots for the GEMM epilogues
+        int n = 0;
+        int* idx = neg_idx_ + (long)frame * strideNeg * kTile;
+        for (int i = 0; i < kTile; ++i)
+            if (sg[i] < 0.0) idx[n++] = i;
+        neg_cnt_[(long)frame * strideNeg] = n;
+    }
+}
+
+// Software-pipelined version of potrf_tile_kernel (experimental, CHEQ_POTRF_PIPE=1): identical arithmetic, but the per-pivot dependency
+// chain (pivot broadcast -> rsqrt -> column scaling) of pivot k + 1 is started by the 16 threads that own column
+// k + 1 as soon as THEY have applied update k to that column, and runs while all other warps are still doing the
+// bulk of update k.  One __syncthreads per pivot as before; the step time drops from chain + update to
+// max(chain, update) + the owners' own share.
+#define POTRF_UPD(a, b, kb) \
+    ((a) > (b) ? true : (a) < (kb) ? true : ((a) == (b) && (a) == (kb)) ? (p_diag || p_row) : (a) == (b) ? p_diag : (a) == (kb) ? p_row : false)
+
+template <int KBN>
+__device__ __forceinline__ void potrf_next_pivot(double (&e)[8][8], int ty, int tx, int ktn, double* ubuf_next,
+                                                 double* dinv, double* sg, ScfState* state, int frame,
+                                                 double pivot_tol) {
+    // executed by the 16 threads with tx == ktn (one half-warp): pivot k' = 16 KBN + ktn
+    const unsigned mask = (tx & 1) ? 0xffff0000u : 0x0000ffffu;
+    const int k = KBN * 16 + ktn;
+    const double d = __shfl_sync(mask, e[KBN][KBN], ktn + 16 * (tx & 1));
+    const double ad = fabs(d);
+    const bool bad = !(ad > pivot_tol) || !(ad < 1.0e30);
+    const double sgnk = (d < 0.0) ? -1.0 : 1.0;
+    double il = rsqrt_pivot(ad);
+    double l = ad * il;
+    {
+        const double res = fma(-l, l, ad);
+        l = fma(0.5 * il, res, l);
+        il = fma(fma(-l, il, 1.0), il, il);
+    }
+    il = bad ? 1.0 : il;
+    l = bad ? 1.0 : l;
+    const double sil = sgnk * il;
+    if (ty == ktn) {
+        dinv[k] = il;
+        sg[k] = sgnk;
+        if (bad && state) atomicExch(&state[frame].info, k + 1);
+    }
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const double v = e[a][KBN];
+        double u = v * sil, keep;
+        if (a < KBN) keep = v * il;
+        else if (a > KBN) keep = u;
+        else {
+            keep = (ty > ktn) ? u : v * il;
+            if (ty == ktn) {
+                u = sil;
+                keep = l;
+            }
+        }
+        e[a][KBN] = keep;
+        ubuf_next[ty + 16 * a] = u;
+    }
+}
+
+template <int KB>
+__device__ __forceinline__ void potrf_pipe_block(double (&e)[8][8], int ty, int tx, bool p_diag, int& cur,
+                                                 double (*ubuf)[kTile], double* dinv, double* sg, ScfState* state,
+                                                 int frame, double pivot_tol) {
+    constexpr int kb = KB;
+    constexpr int bn = (KB < 7) ? KB + 1 : 7;
+    for (int kt = 0; kt < 16; ++kt) {
+        const int k = kb * 16 + kt;
+        const double sk = sg[k];
+        const bool p_row = ty <= kt;    // rows of block kb that are <= k
+        const bool p_col = tx > kt;     // columns of block kb that are > k
+        double su[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) su[a] = sk * ubuf[cur][ty + 16 * a];
+        // ---- owners of column k + 1: bring it up to date and start its pivot ----
+        bool done_same = false, done_next = false;
+        if (kt < 15) {
+            if (tx == kt + 1) {
+                const double uc = ubuf[cur][tx + 16 * kb];
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+                    if (POTRF_UPD(a, kb, kb)) e[a][kb] = fma(-su[a], uc, e[a][kb]);
+                potrf_next_pivot<kb>(e, ty, tx, kt + 1, ubuf[cur ^ 1], dinv, sg, state, frame, pivot_tol);
+                done_same = true;
+            }
+        } else if (KB < 7) {
+            if (tx == 0) {
+                const double uc = ubuf[cur][tx + 16 * bn];
+#pragma unroll
+                for (int a = 0; a < 8; ++a)
+                    if (POTRF_UPD(a, bn, kb)) e[a][bn] = fma(-su[a], uc, e[a][bn]);
+                potrf_next_pivot<bn>(e, ty, tx, 0, ubuf[cur ^ 1], dinv, sg, state, frame, pivot_tol);
+                done_next = true;
+            }
+        }
+        // ---- everybody: the rest of update k ----
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            if (b < kb) continue;                 // columns <= k: finished
+            if (b == kb && (!p_col || done_same)) continue;   // same block: column <= k, or column k + 1 already done
+            if (b == bn && KB < 7 && done_next) continue;
+            const double uc = ubuf[cur][tx + 16 * b];
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+                if (POTRF_UPD(a, b, kb)) e[a][b] = fma(-su[a], uc, e[a][b]);
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+}
+
+__global__ void __launch_bounds__(kPotrfThreads)
+potrf_tile_pipe_kernel(double* A_, long lda, long strideA, double* Minv_, long strideM, double* sgn_, long strideSgn,
+                       int* neg_cnt_, int* neg_idx_, long strideNeg, ScfState* state, double pivot_tol) {
+    const int frame = blockIdx.z;
+    if (state && !state[frame].active) return;
+    extern __shared__ __align__(16) double Ms[];   // staging of M for a coalesced store
+    __shared__ double ubuf[2][kTile];
+    __shared__ double dinv[kTile];
+    __shared__ double sg[kTile];
+    double* A = A_ + (long)frame * strideA;
+    double* Minv = Minv_ + (long)frame * strideM;
+    const int t = threadIdx.x;
+    const int ty = t & 15, tx = t >> 4;
+
+    double e[8][8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b)
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const int r = ty + 16 * a, c = tx + 16 * b;
+            e[a][b] = (r >= c) ? A[r + (long)c * lda] : 0.0;
+        }
+
+    const bool p_diag = ty >= tx;   // within a diagonal 16 x 16 sub-block: element on or below the diagonal
+    int cur = 0;
+    if (tx == 0) potrf_next_pivot<0>(e, ty, tx, 0, ubuf[0], dinv, sg, state, frame, pivot_tol);
+    __syncthreads();
+    potrf_pipe_block<0>(e, ty, tx, p_diag, cur, ubuf, dinv, sg, state, frame, pivot_tol);
+    potrf_pipe_block<1>(e, ty, tx, p_diag, cur, ubuf, dinv, sg, state, frame, pivot_tol);
+    potrf_pipe_block<2>(e, ty, tx, p_diag, cur, ubuf, dinv, sg, state, frame, pivot_tol);
+    potrf_pipe_block<3>(e, ty, tx, p_diag, cur, ubuf, dinv, sg, state, frame, pivot_tol);
+    potrf_pipe_block<4>(e, ty, tx, p_diag, cur, ubuf, dinv, sg, state, frame, pivot_tol);
+    potrf_pipe_block<5>(e, ty, tx, p_diag, cur, ubuf, dinv, sg, state, frame, pivot_tol);
+    potrf_pipe_block<6>(e, ty, tx, p_diag, cur, ubuf, dinv, sg, state, frame, pivot_tol);
+    potrf_pipe_block<7>(e, ty, tx, p_diag, cur, ubuf, dinv, sg, state, frame, pivot_tol);
+
+    // L back to global; M = S X staged through shared memory (M[i][j] = s_i X[i][j], i > j, held as element (j, i))
+#pragma unroll
+    for (int b = 0; b < 8; ++b)
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const int r = ty + 16 * a, c = tx + 16 * b;
+            if (r >= c) A[r + (long)c * lda] = e[a][b];
             double m = 0.0;
             if (r < c) m = sg[c] * e[a][b];
             else if (r == c) m = sg[r] * dinv[r];
@@ -633,8 +829,15 @@ __device__ __forceinline__ void pb_pivot(double (&e)[16], double& myil, int i, i
     const double ad = fabs(d);
     const bool bad = !(ad > pivot_tol) || !(ad < 1.0e30);
     const double sgnk = (d < 0.0) ? -1.0 : 1.0;
-    const double il = bad ? 1.0 : rsqrt_pivot(ad);
-    const double l = bad ? 1.0 : ad * il;
+    double il = rsqrt_pivot(ad);
+    double l = ad * il;
+    {
+        const double res = fma(-l, l, ad);
+        l = fma(0.5 * il, res, l);
+        il = fma(fma(-l, il, 1.0), il, il);
+    }
+    il = bad ? 1.0 : il;
+    l = bad ? 1.0 : l;
     const double sil = sgnk * il;
     if (lane == k) {
         dinv[c0 + k] = il;
@@ -659,8 +862,6 @@ __device__ __forceinline__ void pb_pivot(double (&e)[16], double& myil, int i, i
 }
 
 constexpr int kPB = 16;
-// cycle counters of the blocked diagonal-tile kernel (thread 0 of the CTA): load, phase A, B, C, store, launches
-__device__ unsigned long long g_potrf_cycles[8];
 constexpr int kPbLd = kTile + 1;
 constexpr int kPbSmem = (kTile * kPbLd + kPB * kTile + kPB * kPB + 2 * kTile) * (int)sizeof(double);
 
@@ -1276,6 +1477,22 @@ cudaError_t launch_potrf_tile(double* A, long lda, long strideA, double* Linv, l
         configured = true;
     }
     dim3 grid(1, 1, batch);
+    // the software-pipelined variant (CHEQ_POTRF_PIPE=1) measured 4 % slower than the plain rank-1 kernel: the warp
+    // that owns the next column still executes chain + update back to back (profiles/r1_potrf_variants.txt)
+    static const bool use_v1 = [] { const char* e = getenv("CHEQ_POTRF_PIPE"); return !(e && e[0] == '1'); }();
+    if (use_scalar && use_rank1 && !use_v1) {
+        static bool conf2 = false;
+        if (!conf2) {
+            cudaError_t e = cudaFuncSetAttribute(potrf_tile_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 kPotrfSmem);
+            if (e != cudaSuccess) return e;
+            conf2 = true;
+        }
+        potrf_tile_pipe_kernel<<<grid, kPotrfThreads, kPotrfSmem, stream>>>(A, lda, strideA, Linv, strideLinv, sgn,
+                                                                            strideSgn, neg_cnt, neg_idx, strideNeg,
+                                                                            state, pivot_tol);
+        return cudaGetLastError();
+    }
     if (use_scalar && !use_rank1)
         potrf_tile_blocked_kernel<<<grid, kPotrfThreads, kPbSmem, stream>>>(A, lda, strideA, Linv, strideLinv, sgn,
                                                                                strideSgn, neg_cnt, neg_idx, strideNeg,
