@@ -192,6 +192,7 @@ struct NcclApi {
     int (*CommDestroy)(void*) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
     int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -211,6 +212,23 @@ struct cheq_ctx {
     int tiles_per_panel = 4;
     PanelPlan pplan;
     DeviceBuffer stage, own_list, col_mask, chain;
+    // peer-memory data plane (multi-GPU): the owner's kernels store finished panel tiles straight into the peers'
+    // trapezoids over NVLink; `arena` holds what must be peer-visible besides the trapezoid (signal words, the
+    // diagonal-tile inverses, pivot signs, negative-pivot lists)
+    struct PeerLinks {
+        bool tried = false, enabled = false;
+        int n = 0;                          // world - 1
+        int rank_of[kMaxPeers] = {};
+        void* opened[kMaxPeers][2] = {};    // mappings returned by cudaIpcOpenMemHandle (trapezoid, arena)
+        char* A[kMaxPeers] = {};            // peer trapezoid / arena bases (mapping + offset inside the allocation)
+        char* arena[kMaxPeers] = {};
+        void* local[2] = {nullptr, nullptr};
+        unsigned seq = 0;                   // panels signalled so far (identical on every rank)
+    } links;
+    DeviceBuffer arena, ipc_stage;
+    int p2p_mode = 1;                       // 0: NCCL broadcasts only (CHEQ_DIST_P2P=0)
+    int (*wait_value32)(cudaStream_t, unsigned long long, unsigned, unsigned) = nullptr;
+    int (*mem_address_range)(unsigned long long*, size_t*, unsigned long long) = nullptr;
     double ms_comm_host = 0.0;
     std::mutex mu;
     std::string err;
@@ -504,6 +522,7 @@ struct Dense {
     long strideNeg;
     double flops = 0.0;
     const struct SplitPlan* plan = nullptr;   // wave-aware recursion splits (nullptr: halve)
+    bool push = false;                        // panel outputs are also stored into the peers' memory
 };
 
 
@@ -563,8 +582,22 @@ int factor_panel(Dense& D, int j0, int n) {
         double* Ajj = D.A + (long)j0 + (long)j0 * D.ld;
         double* Lk = D.Linv + (long)(j0 / kTile) * kTile * kTile;
         if (int rcp = prof_begin(ctx, 1)) return rcp;
+        PotrfPeers pp{};
+        if (D.push) {
+            const cheq_ctx::PeerLinks& lk = ctx->links;
+            pp.n = lk.n;
+            for (int i = 0; i < lk.n; ++i) {
+                // the arena-backed arrays of the peers sit at the same offsets as ours
+                pp.A[i] = (double*)lk.A[i] + (Ajj - D.A);
+                pp.Minv[i] = (double*)(lk.arena[i] + ((char*)Lk - ctx->arena.as<char>()));
+                pp.sgn[i] = (double*)(lk.arena[i] + ((char*)(D.sgn + j0) - ctx->arena.as<char>()));
+                pp.neg_cnt[i] = (int*)(lk.arena[i] + ((char*)(D.neg_cnt + j0 / kTile) - ctx->arena.as<char>()));
+                pp.neg_idx[i] = (int*)(lk.arena[i] + ((char*)(D.neg_idx + (long)j0) - ctx->arena.as<char>()));
+            }
+        }
         LAUNCH(launch_potrf_tile(Ajj, D.ld, D.strideA, Lk, D.strideLinv, D.sgn + j0, D.strideSgn, D.neg_cnt + j0 / kTile,
-                                 D.neg_idx + (long)j0, D.strideNeg, D.state, kPivotTol, D.batch, ctx->cur));
+                                 D.neg_idx + (long)j0, D.strideNeg, D.state, kPivotTol, D.batch, ctx->cur,
+                                 D.push ? &pp : nullptr));
         if (int rcp = prof_end(ctx)) return rcp;
         const int mt = (D.MT - j0 - kTile) / kTile;
         if (mt > 0) {
@@ -582,6 +615,10 @@ int factor_panel(Dense& D, int j0, int n) {
             g.lower = 0;
             g.subtract = 0;
             g.state = D.state;
+            if (D.push) {
+                g.n_peers = ctx->links.n;
+                for (int i = 0; i < g.n_peers; ++i) g.peerC[i] = (double*)ctx->links.A[i] + (g.C - D.A);
+            }
             const int rc2 = launch_gemm_timed(ctx, g, mt, 1, D.batch, 2.0 * mt * kTile * (double)kTile * kTile);
             if (rc2) return rc2;
         }
@@ -698,11 +735,12 @@ bool nccl_load(std::string& err) {
     api.CommDestroy = (int (*)(void*))sym("ncclCommDestroy");
     api.Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclBroadcast");
     api.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))sym("ncclAllReduce");
+    api.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))sym("ncclAllGather");
     api.GroupStart = (int (*)())sym("ncclGroupStart");
     api.GroupEnd = (int (*)())sym("ncclGroupEnd");
     api.GetErrorString = (const char* (*)(int))sym("ncclGetErrorString");
     if (!api.GetUniqueId || !api.CommInitRank || !api.CommDestroy || !api.Broadcast || !api.AllReduce ||
-        !api.GroupStart || !api.GroupEnd || !api.GetErrorString)
+        !api.AllGather || !api.GroupStart || !api.GroupEnd || !api.GetErrorString)
         return false;
     api.handle = h;
     g_nccl = api;
@@ -732,6 +770,130 @@ int ensure_panel_plan(cheq_ctx* ctx, const Layout& L) {
     if (!pp.own_tiles.empty())
         CU(cudaMemcpy(ctx->own_list.p, pp.own_tiles.data(), pp.own_tiles.size() * sizeof(int), cudaMemcpyHostToDevice));
     CU(cudaMemcpy(ctx->col_mask.p, pp.mask.data(), pp.mask.size(), cudaMemcpyHostToDevice));
+    return CHEQ_OK;
+}
+
+// ---- peer-memory data plane ----------------------------------------------------------------------------------
+// Layout of the arena for a padded size NP: signal words, then Linv (NP x 128), sgn (NP), negative-pivot counts
+// (NP / 128) and lists (NP).  Identical on every rank, so a local offset is also the peer's offset.
+struct ArenaLayout {
+    size_t linv, sgn, neg_cnt, neg_idx, bytes;
+    explicit ArenaLayout(long NP) {
+        linv = 4096;
+        sgn = linv + (size_t)NP * kTile * 8;
+        neg_cnt = sgn + (size_t)NP * 8;
+        neg_idx = neg_cnt + (((size_t)(NP / kTile) * 4 + 255) / 256) * 256;
+        bytes = neg_idx + (size_t)NP * 4;
+        bytes = std::max<size_t>(bytes, (size_t)8 << 20);   // its own allocation, never a sub-allocation
+    }
+};
+
+void p2p_close(cheq_ctx* ctx) {
+    cheq_ctx::PeerLinks& lk = ctx->links;
+    for (int i = 0; i < kMaxPeers; ++i)
+        for (int k = 0; k < 2; ++k)
+            if (lk.opened[i][k]) {
+                cudaIpcCloseMemHandle(lk.opened[i][k]);
+                lk.opened[i][k] = nullptr;
+            }
+    lk.enabled = false;
+}
+
+struct IpcRecord {
+    cudaIpcMemHandle_t handle[2];
+    unsigned long long offset[2];
+    int ok;
+    int pad;
+};
+
+// Start-of-solve rendezvous of a group: a barrier (no rank may push into a peer that is still reading its factor
+// from the previous solve) that also (re)establishes the peer mappings when any rank's buffers moved.
+int p2p_setup(cheq_ctx* ctx) {
+    cheq_ctx::PeerLinks& lk = ctx->links;
+    cudaStream_t ms = ctx->stream, ps = ctx->panel_stream;
+    const int world = ctx->world, rank = ctx->rank;
+    if (!lk.tried) {
+        if (const char* env = getenv("CHEQ_DIST_P2P")) ctx->p2p_mode = atoi(env) != 0;
+        cudaDriverEntryPointQueryResult q;
+        void* fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            ctx->wait_value32 = (int (*)(cudaStream_t, unsigned long long, unsigned, unsigned))fn;
+        fn = nullptr;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            ctx->mem_address_range = (int (*)(unsigned long long*, size_t*, unsigned long long))fn;
+        cudaGetLastError();
+        if (!ctx->wait_value32 || !ctx->mem_address_range || world - 1 > kMaxPeers) ctx->p2p_mode = 0;
+    }
+    void* local[2] = {ctx->A.p, ctx->arena.p};
+    int changed = (!lk.tried || local[0] != lk.local[0] || local[1] != lk.local[1]) ? 1 : 0;
+    lk.tried = true;
+    CU(ctx->ipc_stage.ensure(4096 + (size_t)world * sizeof(IpcRecord)));
+    int* d_flag = ctx->ipc_stage.as<int>();
+    CU(cudaEventRecord(ctx->ev_ready, ms));
+    CU(cudaStreamWaitEvent(ps, ctx->ev_ready, 0));
+    CU(cudaMemcpyAsync(d_flag, &changed, sizeof(int), cudaMemcpyHostToDevice, ps));
+    NC(g_nccl.AllReduce(d_flag, d_flag, 1, kNcclInt, kNcclMax, ctx->comm, ps));
+    CU(cudaMemcpyAsync(&changed, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ps));
+    CU(cudaStreamSynchronize(ps));
+    if (!changed || !ctx->p2p_mode) {
+        if (!ctx->p2p_mode) lk.enabled = false;
+        return CHEQ_OK;
+    }
+    // some rank's buffers moved: everybody re-exports and re-imports
+    p2p_close(ctx);
+    IpcRecord mine{};
+    mine.ok = 1;
+    for (int k = 0; k < 2; ++k) {
+        unsigned long long base = 0;
+        size_t size = 0;
+        if (ctx->mem_address_range(&base, &size, (unsigned long long)local[k]) != 0 ||
+            cudaIpcGetMemHandle(&mine.handle[k], (void*)base) != cudaSuccess) {
+            cudaGetLastError();
+            mine.ok = 0;
+            break;
+        }
+        mine.offset[k] = (unsigned long long)local[k] - base;
+    }
+    char* d_all = ctx->ipc_stage.as<char>() + 4096;
+    CU(cudaMemcpyAsync(d_all + (size_t)rank * sizeof(IpcRecord), &mine, sizeof(IpcRecord), cudaMemcpyHostToDevice, ps));
+    NC(g_nccl.AllGather(d_all + (size_t)rank * sizeof(IpcRecord), d_all, sizeof(IpcRecord), kNcclChar, ctx->comm, ps));
+    std::vector<IpcRecord> all(world);
+    CU(cudaMemcpyAsync(all.data(), d_all, (size_t)world * sizeof(IpcRecord), cudaMemcpyDeviceToHost, ps));
+    CU(cudaStreamSynchronize(ps));
+    int ok = 1;
+    for (int r = 0; r < world; ++r) ok &= all[r].ok;
+    lk.n = 0;
+    for (int r = 0; r < world && ok; ++r) {
+        if (r == rank) continue;
+        const int i = lk.n;
+        for (int k = 0; k < 2; ++k) {
+            void* mapped = nullptr;
+            if (cudaIpcOpenMemHandle(&mapped, all[r].handle[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = 0;
+                break;
+            }
+            lk.opened[i][k] = mapped;
+            (k == 0 ? lk.A[i] : lk.arena[i]) = (char*)mapped + all[r].offset[k];
+        }
+        lk.rank_of[i] = r;
+        if (ok) lk.n++;
+    }
+    // every rank must have succeeded, or nobody uses the peer path
+    CU(cudaMemcpyAsync(d_flag, &ok, sizeof(int), cudaMemcpyHostToDevice, ps));
+    NC(g_nccl.AllReduce(d_flag, d_flag, 1, kNcclInt, 3 /* ncclMin */, ctx->comm, ps));
+    CU(cudaMemcpyAsync(&ok, d_flag, sizeof(int), cudaMemcpyDeviceToHost, ps));
+    CU(cudaStreamSynchronize(ps));
+    if (!ok) {
+        p2p_close(ctx);
+        ctx->p2p_mode = 0;
+    } else {
+        lk.enabled = true;
+    }
+    lk.local[0] = local[0];
+    lk.local[1] = local[1];
     return CHEQ_OK;
 }
 
@@ -788,39 +950,58 @@ int factor_blocked(Dense& D, int p_begin, int p_end) {
         const int j0 = pp.begin[p] * kTile, n = (pp.end[p] - pp.begin[p]) * kTile;
         const long rows = D.MT - j0;
         const bool mine = pp.owner[p] == ctx->rank;
+        const bool push = ctx->world > 1 && ctx->links.enabled;
         if (mine) {
             CU(cudaStreamWaitEvent(ps, ctx->ev_ready, 0));
             const SplitPlan* saved = D.plan;
             D.plan = nullptr;   // panels are a few tiles wide: plain halving
             ctx->cur = ps;
+            D.push = push;
             const int rc = factor_panel(D, j0, n);
+            D.push = false;
             ctx->cur = ms;
             D.plan = saved;
             if (rc) return rc;
         }
-        if (ctx->world > 1) {
-            auto t0 = Clock::now();
-            double* stage = ctx->stage.as<double>();
-            double* Ap = D.A + (long)j0 + (long)j0 * D.ld;
-            if (mine)
-                CU(cudaMemcpy2DAsync(stage, rows * 8, Ap, D.ld * 8, rows * 8, n, cudaMemcpyDeviceToDevice, ps));
-            double* Lk = D.Linv + (long)(j0 / kTile) * kTile * kTile;
-            const int root = pp.owner[p];
-            NC(g_nccl.GroupStart());
-            NC(g_nccl.Broadcast(stage, stage, (size_t)rows * n, kNcclDouble, root, ctx->comm, ps));
-            NC(g_nccl.Broadcast(Lk, Lk, (size_t)n * kTile, kNcclDouble, root, ctx->comm, ps));
-            NC(g_nccl.Broadcast(D.sgn + j0, D.sgn + j0, (size_t)n, kNcclDouble, root, ctx->comm, ps));
-            NC(g_nccl.Broadcast(D.neg_cnt + j0 / kTile, D.neg_cnt + j0 / kTile, (size_t)n / kTile, kNcclInt, root,
-                                ctx->comm, ps));
-            NC(g_nccl.Broadcast(D.neg_idx + j0, D.neg_idx + j0, (size_t)n, kNcclInt, root, ctx->comm, ps));
-            NC(g_nccl.GroupEnd());
-            if (!mine)
-                CU(cudaMemcpy2DAsync(Ap, D.ld * 8, stage, rows * 8, rows * 8, n, cudaMemcpyDeviceToDevice, ps));
-            ctx->launches += 1;
-            ctx->ms_comm_host += ms_since(t0);
+        if (push) {
+            // data plane = peer stores issued by the owner's kernels; what is left is one flag per peer
+            const unsigned seq = ++ctx->links.seq;
+            if (mine) {
+                unsigned* words[kMaxPeers];
+                for (int i = 0; i < ctx->links.n; ++i) words[i] = (unsigned*)ctx->links.arena[i] + ctx->rank;
+                LAUNCH(launch_signal_peers(words, ctx->links.n, seq, ps));
+                CU(cudaEventRecord(ctx->ev_bcast, ps));
+                CU(cudaStreamWaitEvent(ms, ctx->ev_bcast, 0));
+            } else {
+                const unsigned long long addr = (unsigned long long)(ctx->arena.as<unsigned>() + pp.owner[p]);
+                if (ctx->wait_value32(ms, addr, seq, 0 /* CU_STREAM_WAIT_VALUE_GEQ */) != 0)
+                    return fail(ctx, CHEQ_ERR_CUDA, "cuStreamWaitValue32 failed");
+            }
+        } else {
+            if (ctx->world > 1) {
+                auto t0 = Clock::now();
+                double* stage = ctx->stage.as<double>();
+                double* Ap = D.A + (long)j0 + (long)j0 * D.ld;
+                if (mine)
+                    CU(cudaMemcpy2DAsync(stage, rows * 8, Ap, D.ld * 8, rows * 8, n, cudaMemcpyDeviceToDevice, ps));
+                double* Lk = D.Linv + (long)(j0 / kTile) * kTile * kTile;
+                const int root = pp.owner[p];
+                NC(g_nccl.GroupStart());
+                NC(g_nccl.Broadcast(stage, stage, (size_t)rows * n, kNcclDouble, root, ctx->comm, ps));
+                NC(g_nccl.Broadcast(Lk, Lk, (size_t)n * kTile, kNcclDouble, root, ctx->comm, ps));
+                NC(g_nccl.Broadcast(D.sgn + j0, D.sgn + j0, (size_t)n, kNcclDouble, root, ctx->comm, ps));
+                NC(g_nccl.Broadcast(D.neg_cnt + j0 / kTile, D.neg_cnt + j0 / kTile, (size_t)n / kTile, kNcclInt, root,
+                                    ctx->comm, ps));
+                NC(g_nccl.Broadcast(D.neg_idx + j0, D.neg_idx + j0, (size_t)n, kNcclInt, root, ctx->comm, ps));
+                NC(g_nccl.GroupEnd());
+                if (!mine)
+                    CU(cudaMemcpy2DAsync(Ap, D.ld * 8, stage, rows * 8, rows * 8, n, cudaMemcpyDeviceToDevice, ps));
+                ctx->launches += 1;
+                ctx->ms_comm_host += ms_since(t0);
+            }
+            CU(cudaEventRecord(ctx->ev_bcast, ps));
+            CU(cudaStreamWaitEvent(ms, ctx->ev_bcast, 0));
         }
-        CU(cudaEventRecord(ctx->ev_bcast, ps));
-        CU(cudaStreamWaitEvent(ms, ctx->ev_bcast, 0));
         // trailing update of the owned tile columns right of the panel
         const int e = pp.end[p];
         const int pos = (int)(std::lower_bound(pp.own_tiles.begin(), pp.own_tiles.end(), e) - pp.own_tiles.begin());
@@ -1120,7 +1301,21 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
     const bool blocked = use_blocked(ctx, batch);
     const bool dist = blocked && ctx->world > 1;
     const PanelPlan& pp = ctx->pplan;
-    if (dist) CU(ctx->stage.ensure((size_t)L.MT * ctx->tiles_per_panel * kTile * 8));
+    if (dist) {
+        // what the peers must see besides the trapezoid lives in one arena with the same layout on every rank
+        const ArenaLayout AL(L.NP);
+        const void* before = ctx->arena.p;
+        CU(ctx->arena.ensure(AL.bytes));
+        if (ctx->arena.p != before) CU(cudaMemsetAsync(ctx->arena.p, 0, 4096, st));   // fresh signal words
+        char* ar = ctx->arena.as<char>();
+        D.Linv = (double*)(ar + AL.linv);
+        D.sgn = (double*)(ar + AL.sgn);
+        D.neg_cnt = (int*)(ar + AL.neg_cnt);
+        D.neg_idx = (int*)(ar + AL.neg_idx);
+        rc = p2p_setup(ctx);   // start-of-solve barrier + peer mappings
+        if (rc) return rc;
+        if (!ctx->links.enabled) CU(ctx->stage.ensure((size_t)L.MT * ctx->tiles_per_panel * kTile * 8));
+    }
     const uint8_t* mask_h = dist ? ctx->col_mask.as<uint8_t>() + L.nxp / kTile : nullptr;
 
     if (!L.scf) {
@@ -1180,7 +1375,7 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
             LAUNCH(launch_copy_lower_tiles(ctx->S0.as<double>(), ld0, stride0, Ahh, L.ld, D.strideA, mt_h, nt_h,
                                            D.state, batch, st, mask_h));
         LAUNCH(launch_set_h_diagonal(Ahh, L.ld, D.strideA, ctx->S0.as<double>(), ld0, stride0, hard_h,
-                                     q + L.nxp, L.NP, type_h, L.nhp, D.state, batch, st));
+                                     q + L.nxp, L.NP, type_h, L.nhp, D.state, batch, st, mask_h));
         D.flops = 0.0;
         rc = blocked ? factor_blocked(D, pp.x_panels, (int)pp.begin.size()) : factor_panel(D, L.nxp, L.nhp);
         if (rc) return rc;
@@ -1200,6 +1395,9 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
             NC(g_nccl.Broadcast(D.state, D.state, sizeof(ScfState), kNcclChar, 0, ctx->comm, ps));
             NC(g_nccl.Broadcast(ctx->active.p, ctx->active.p, sizeof(int), kNcclChar, 0, ctx->comm, ps));
             NC(g_nccl.Broadcast(q, q, (size_t)L.NP, kNcclDouble, 0, ctx->comm, ps));
+            // barrier: every rank has finished reading this iteration's factor before any owner pushes the next one
+            NC(g_nccl.AllReduce(ctx->ipc_stage.as<int>() + 16, ctx->ipc_stage.as<int>() + 16, 1, kNcclInt, kNcclMax,
+                                ctx->comm, ps));
             NC(g_nccl.GroupEnd());
             CU(cudaMemcpyAsync(ctx->h_active, ctx->active.p, sizeof(int), cudaMemcpyDeviceToHost, ps));
             CU(cudaStreamSynchronize(ps));
@@ -1465,6 +1663,9 @@ void cheq_ctx_destroy(cheq_ctx* ctx) {
     ctx->own_list.release();
     ctx->col_mask.release();
     ctx->chain.release();
+    p2p_close(ctx);
+    ctx->arena.release();
+    ctx->ipc_stage.release();
     if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
     if (ctx->ev_bcast) cudaEventDestroy(ctx->ev_bcast);
     if (ctx->panel_stream) cudaStreamDestroy(ctx->panel_stream);

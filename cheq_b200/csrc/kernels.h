@@ -41,6 +41,8 @@ struct GatherArgs {
     double *x, *y, *z, *diag, *chi, *hard;
 };
 
+constexpr int kMaxPeers = 7;   // one node: up to 8 GPUs
+
 struct GemmArgs {
     const double* A;           // m x K, column-major
     const double* B;           // n x K, column-major
@@ -62,6 +64,21 @@ struct GemmArgs {
     // (used by the `lower` test).  nullptr: identity.
     const int* n_list;
     int row0;
+    // Peer push (multi-GPU panel factorisation): every C tile is ALSO stored at the same offset of each peer's
+    // trapezoid (peer-mapped pointers over NVLink), so the finished panel reaches the other ranks tile by tile
+    // while the owner is still factoring -- no pack / broadcast / unpack afterwards.
+    int n_peers;
+    double* peerC[kMaxPeers];   // peer bases corresponding to C
+};
+
+// Peer destinations of one diagonal tile's outputs (pointers already offset to the tile)
+struct PotrfPeers {
+    int n;
+    double* A[kMaxPeers];
+    double* Minv[kMaxPeers];
+    double* sgn[kMaxPeers];
+    int* neg_cnt[kMaxPeers];
+    int* neg_idx[kMaxPeers];
 };
 
 int assemble_smem_bytes(int table_bytes, int* table_smem_bytes);
@@ -89,7 +106,9 @@ void set_gemm_warps(int warps);   // tuning knob: 8 or 16 warps per GEMM CTA
 // |pivot| <= pivot_tol sets state.info (the caller then falls back to the pivoted LU).
 cudaError_t launch_potrf_tile(double* A, long lda, long strideA, double* Linv, long strideLinv, double* sgn,
                               long strideSgn, int* neg_cnt, int* neg_idx, long strideNeg, ScfState* state,
-                              double pivot_tol, int batch, cudaStream_t stream);
+                              double pivot_tol, int batch, cudaStream_t stream, const PotrfPeers* peers = nullptr);
+// release-store `value` into each peer's signal word (after a system-scope fence)
+cudaError_t launch_signal_peers(unsigned* const* peer_words, int n_peers, unsigned value, cudaStream_t stream);
 // copies the tiles on/below the diagonal of an (m_tiles x n_tiles) tile region
 // col_mask (nullable): one flag per tile column of the region, 0 = skip (columns owned by another rank)
 cudaError_t launch_copy_lower_tiles(const double* src, long lds, long stride_src, double* dst, long ldd,
@@ -98,7 +117,8 @@ cudaError_t launch_copy_lower_tiles(const double* src, long lds, long stride_src
 // A_ii = S0_ii + hardness_i * kHChargeFactor * clamp(q_i, -0.95, 0.95) for the real atoms of the hydrogen block
 cudaError_t launch_set_h_diagonal(double* A, long lda, long strideA, const double* S0, long ld0, long stride0,
                                   const double* hard_h, const double* q_h, long q_stride, const uint8_t* type_h,
-                                  int nhp, const ScfState* state, int batch, cudaStream_t stream);
+                                  int nhp, const ScfState* state, int batch, cudaStream_t stream,
+                                  const uint8_t* col_mask = nullptr);
 // mu = (f1.fc - Q) / (f1.f1) from rows NP, NP+1; v = fc - mu f1
 cudaError_t launch_mu(const double* A, long lda, long strideA, int NP, double total_charge, double* v,
                       long v_stride, const double* sgn, long strideSgn, ScfState* state, int batch,

@@ -65,7 +65,7 @@ constexpr int kGroupM = 8;   // tile rows per rasterisation group: their A slabs
 // FM = 16-row fragments per warp, WM = warps along M: CTA tile (16 FM WM) x 128.
 //   <4, 2>: 128 x 128, 8 warps (64 x 32 warp tiles)      <2, 4>: 128 x 128, 16 warps (32 x 32)
 //   <2, 2>:  64 x 128, 8 warps: twice the CTAs for skinny updates that would otherwise leave SMs idle
-template <int FM, int WM>
+template <int FM, int WM, bool PEERS = false>
 __global__ void __launch_bounds__(WM * 4 * 32, 1) gemm_nt_kernel(GemmArgs g) {
     constexpr int kWarpsM = WM;
     constexpr int kThreads = kWarpsM * 4 * 32;        // 256 or 512
@@ -213,6 +213,10 @@ __global__ void __launch_bounds__(WM * 4 * 32, 1) gemm_nt_kernel(GemmArgs g) {
                         v.y = old.y - v.y;
                     }
                     *p = v;
+                    if constexpr (PEERS) {
+                        const long off = (long)((double*)p - g.C);
+                        for (int pe = 0; pe < g.n_peers; ++pe) *(double2*)(g.peerC[pe] + off) = v;
+                    }
                 }
     }
 }
@@ -249,7 +253,7 @@ constexpr int kPotrfSmem = kTile * kPotrfLd * (int)sizeof(double);
 
 __global__ void __launch_bounds__(kPotrfThreads)
 potrf_tile_kernel(double* A_, long lda, long strideA, double* Minv_, long strideM, double* sgn_, long strideSgn,
-                  int* neg_cnt_, int* neg_idx_, long strideNeg, ScfState* state, double pivot_tol) {
+                  int* neg_cnt_, int* neg_idx_, long strideNeg, ScfState* state, double pivot_tol, PotrfPeers peers) {
     const int frame = blockIdx.z;
     if (state && !state[frame].active) return;
     extern __shared__ __align__(16) double Ms[];   // staging of M for a coalesced store
@@ -381,7 +385,10 @@ potrf_tile_kernel(double* A_, long lda, long strideA, double* Minv_, long stride
 #pragma unroll
         for (int a = 0; a < 8; ++a) {
             const int r = ty + 16 * a, c = tx + 16 * b;
-            if (r >= c) A[r + (long)c * lda] = e[a][b];
+            if (r >= c) {
+                A[r + (long)c * lda] = e[a][b];
+                for (int pe = 0; pe < peers.n; ++pe) peers.A[pe][r + (long)c * lda] = e[a][b];
+            }
             // Ms[j * ld + i] = M[i][j]; the holder of (r, c) fills M[c][r]: X part below the diagonal of M,
             // the diagonal, and zeros above it
             double m = 0.0;
@@ -392,15 +399,24 @@ potrf_tile_kernel(double* A_, long lda, long strideA, double* Minv_, long stride
     __syncthreads();
     for (int idx = t; idx < kTile * kTile; idx += kPotrfThreads) {
         const int i = idx & (kTile - 1), j = idx >> 7;
-        Minv[idx] = Ms[j * kPotrfLd + i];
+        const double m = Ms[j * kPotrfLd + i];
+        Minv[idx] = m;
+        for (int pe = 0; pe < peers.n; ++pe) peers.Minv[pe][idx] = m;
     }
-    if (t < kTile && sgn_) sgn_[(long)frame * strideSgn + t] = sg[t];
+    if (t < kTile && sgn_) {
+        sgn_[(long)frame * strideSgn + t] = sg[t];
+        for (int pe = 0; pe < peers.n; ++pe) peers.sgn[pe][t] = sg[t];
+    }
     if (t == 0 && neg_cnt_) {   // compact list of this tile's negative pivots for the GEMM epilogues
         int n = 0;
         int* idx = neg_idx_ + (long)frame * strideNeg * kTile;
         for (int i = 0; i < kTile; ++i)
-            if (sg[i] < 0.0) idx[n++] = i;
+            if (sg[i] < 0.0) {
+                for (int pe = 0; pe < peers.n; ++pe) peers.neg_idx[pe][n] = i;
+                idx[n++] = i;
+            }
         neg_cnt_[(long)frame * strideNeg] = n;
+        for (int pe = 0; pe < peers.n; ++pe) peers.neg_cnt[pe][0] = n;
     }
 }
 
@@ -1014,10 +1030,11 @@ copy_lower_tiles_kernel(const double* src, long lds, long stride_src, double* ds
 
 __global__ void set_h_diagonal_kernel(double* A, long lda, long strideA, const double* S0, long ld0,
                                       long stride0, const double* hard_h, const double* q_h, long q_stride,
-                                      const uint8_t* type_h, int nhp, const ScfState* state) {
+                                      const uint8_t* type_h, int nhp, const ScfState* state, const uint8_t* col_mask) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const int frame = blockIdx.z;
     if (i >= nhp) return;
+    if (col_mask && !col_mask[i / kTile]) return;   // column owned by another rank
     if (state && !state[frame].active) return;
     if (type_h[i] == kPadType) return;
     // implementation.rs:567-572: hardness * (1 + clamp(q, -0.95, 0.95) * H_CHARGE_DEPENDENCE_FACTOR)
@@ -1431,12 +1448,26 @@ cudaError_t launch_gemm_nt(const GemmArgs& g, int m_tiles, int n_tiles, int batc
             e = cudaFuncSetAttribute(gemm_nt_kernel<2, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(gemm_nt_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(gemm_nt_kernel<2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(gemm_nt_kernel<2, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
         if (e != cudaSuccess) return e;
         configured = true;
     }
     // skinny problems: 64-row tiles double the CTA count when 128-row tiles would leave SMs idle
     const long tiles128 = g.lower ? (long)m_tiles * n_tiles - (long)n_tiles * (n_tiles - 1) / 2 : (long)m_tiles * n_tiles;
     const bool half = (g_gemm_half_tiles < 0) ? (tiles128 * batch <= 74) : (g_gemm_half_tiles != 0);
+    if (args.n_peers > 0) {   // leaf solves of a distributed panel: tiles are also pushed to the peers
+        if (half) {
+            args.m_tiles = 2 * m_tiles;
+            grid.x = 2 * m_tiles * n_tiles;
+            gemm_nt_kernel<2, 2, true><<<grid, 256, kGemmSmem, stream>>>(args);
+        } else {
+            gemm_nt_kernel<2, 4, true><<<grid, 512, kGemmSmem, stream>>>(args);
+        }
+        return cudaGetLastError();
+    }
     if (half) {
         args.m_tiles = 2 * m_tiles;
         grid.x = 2 * m_tiles * n_tiles;
@@ -1449,9 +1480,31 @@ cudaError_t launch_gemm_nt(const GemmArgs& g, int m_tiles, int n_tiles, int batc
     return cudaGetLastError();
 }
 
+__global__ void signal_peers_kernel(PotrfPeers words, unsigned value) {
+    // the panel's tiles were pushed by earlier kernels of this stream; the fence orders this (system-scope) flag
+    // store after them for observers on other GPUs
+    __threadfence_system();
+    const int pe = threadIdx.x;
+    if (pe < words.n) {
+        volatile unsigned* w = (volatile unsigned*)words.neg_cnt[pe];
+        *w = value;
+    }
+    __threadfence_system();
+}
+
+cudaError_t launch_signal_peers(unsigned* const* peer_words, int n_peers, unsigned value, cudaStream_t stream) {
+    PotrfPeers w{};
+    w.n = n_peers;
+    for (int i = 0; i < n_peers; ++i) w.neg_cnt[i] = (int*)peer_words[i];
+    signal_peers_kernel<<<1, 32, 0, stream>>>(w, value);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_potrf_tile(double* A, long lda, long strideA, double* Linv, long strideLinv, double* sgn,
                               long strideSgn, int* neg_cnt, int* neg_idx, long strideNeg, ScfState* state,
-                              double pivot_tol, int batch, cudaStream_t stream) {
+                              double pivot_tol, int batch, cudaStream_t stream, const PotrfPeers* peers) {
+    PotrfPeers pp{};
+    if (peers) pp = *peers;
     static bool configured = false;
     // CHEQ_POTRF_DMMA=1 selects the rank-4 DMMA variant.  Measured on B200 (profiles/r1_potrf_variants.txt): it is
     // 2x SLOWER than the rank-1 DFMA kernel (132 vs 66 us per tile) because ptxas keeps part of the 128-register
@@ -1480,6 +1533,11 @@ cudaError_t launch_potrf_tile(double* A, long lda, long strideA, double* Linv, l
     // the software-pipelined variant (CHEQ_POTRF_PIPE=1) measured 4 % slower than the plain rank-1 kernel: the warp
     // that owns the next column still executes chain + update back to back (profiles/r1_potrf_variants.txt)
     static const bool use_v1 = [] { const char* e = getenv("CHEQ_POTRF_PIPE"); return !(e && e[0] == '1'); }();
+    if (pp.n > 0) {   // only the default kernel knows how to push its outputs to peers
+        potrf_tile_kernel<<<grid, kPotrfThreads, kPotrfSmem, stream>>>(A, lda, strideA, Linv, strideLinv, sgn, strideSgn,
+                                                                       neg_cnt, neg_idx, strideNeg, state, pivot_tol, pp);
+        return cudaGetLastError();
+    }
     if (use_scalar && use_rank1 && !use_v1) {
         static bool conf2 = false;
         if (!conf2) {
@@ -1499,7 +1557,7 @@ cudaError_t launch_potrf_tile(double* A, long lda, long strideA, double* Linv, l
                                                                                state, pivot_tol);
     else if (use_scalar)
         potrf_tile_kernel<<<grid, kPotrfThreads, kPotrfSmem, stream>>>(A, lda, strideA, Linv, strideLinv, sgn, strideSgn,
-                                                                       neg_cnt, neg_idx, strideNeg, state, pivot_tol);
+                                                                       neg_cnt, neg_idx, strideNeg, state, pivot_tol, pp);
     else
         potrf_tile_dmma_kernel<<<grid, kPotrfThreads, kPotrfSmem, stream>>>(A, lda, strideA, Linv, strideLinv, sgn,
                                                                             strideSgn, neg_cnt, neg_idx, strideNeg,
@@ -1518,11 +1576,12 @@ cudaError_t launch_copy_lower_tiles(const double* src, long lds, long stride_src
 
 cudaError_t launch_set_h_diagonal(double* A, long lda, long strideA, const double* S0, long ld0, long stride0,
                                   const double* hard_h, const double* q_h, long q_stride, const uint8_t* type_h,
-                                  int nhp, const ScfState* state, int batch, cudaStream_t stream) {
+                                  int nhp, const ScfState* state, int batch, cudaStream_t stream,
+                                  const uint8_t* col_mask) {
     if (nhp <= 0) return cudaSuccess;
     dim3 grid((nhp + 255) / 256, 1, batch);
     set_h_diagonal_kernel<<<grid, 256, 0, stream>>>(A, lda, strideA, S0, ld0, stride0, hard_h, q_h, q_stride,
-                                                    type_h, nhp, state);
+                                                    type_h, nhp, state, col_mask);
     return cudaGetLastError();
 }
 
