@@ -13,7 +13,7 @@ python - <<PY
 import json
 for f in ("gpurun_out/bench_dist${N}_p2p.json", "gpurun_out/bench_dist${N}_nccl.json"):
     try:
-        d = json.load(open(f)); r = d["roofline"]
+        d = json.loads([l for l in open(f) if l.startswith("{")][-1]); r = d["roofline"]
         print(f, "value", round(d["value"], 4), "e2e", round(d["e2e"]["value"], 4), "scf_ms", round(d["config"]["phases_ms"]["ms_scf"], 1),
               "once", round(d["config"]["phases_ms"]["ms_factor_once"], 1), "md", round(d["secondary"]["md"]["frames_per_s"]))
     except Exception as e:
