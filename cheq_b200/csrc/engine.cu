@@ -226,7 +226,8 @@ struct cheq_ctx {
         unsigned seq = 0;                   // panels signalled so far (identical on every rank)
     } links;
     DeviceBuffer arena, ipc_stage;
-    int p2p_mode = 1;                       // 0: NCCL broadcasts only (CHEQ_DIST_P2P=0)
+    int p2p_mode = 1;                       // CHEQ_DIST_P2P: 0 NCCL broadcasts only, 1 automatic, 2 always push
+    bool push_now = false;                  // decision for the current solve
     int (*wait_value32)(cudaStream_t, unsigned long long, unsigned, unsigned) = nullptr;
     int (*mem_address_range)(unsigned long long*, size_t*, unsigned long long) = nullptr;
     double ms_comm_host = 0.0;
@@ -813,7 +814,7 @@ int p2p_setup(cheq_ctx* ctx) {
     cudaStream_t ms = ctx->stream, ps = ctx->panel_stream;
     const int world = ctx->world, rank = ctx->rank;
     if (!lk.tried) {
-        if (const char* env = getenv("CHEQ_DIST_P2P")) ctx->p2p_mode = atoi(env) != 0;
+        if (const char* env = getenv("CHEQ_DIST_P2P")) ctx->p2p_mode = std::max(0, std::min(2, atoi(env)));
         cudaDriverEntryPointQueryResult q;
         void* fn = nullptr;
         if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q) == cudaSuccess &&
@@ -950,7 +951,7 @@ int factor_blocked(Dense& D, int p_begin, int p_end) {
         const int j0 = pp.begin[p] * kTile, n = (pp.end[p] - pp.begin[p]) * kTile;
         const long rows = D.MT - j0;
         const bool mine = pp.owner[p] == ctx->rank;
-        const bool push = ctx->world > 1 && ctx->links.enabled;
+        const bool push = ctx->world > 1 && ctx->push_now;
         if (mine) {
             CU(cudaStreamWaitEvent(ps, ctx->ev_ready, 0));
             const SplitPlan* saved = D.plan;
@@ -1314,7 +1315,14 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
         D.neg_idx = (int*)(ar + AL.neg_idx);
         rc = p2p_setup(ctx);   // start-of-solve barrier + peer mappings
         if (rc) return rc;
-        if (!ctx->links.enabled) CU(ctx->stage.ensure((size_t)L.MT * ctx->tiles_per_panel * kTile * 8));
+        // Data plane for this solve.  Pushing from the epilogues costs (world - 1) unicast copies of every panel on
+        // the owner's critical path; a broadcast costs one copy after the panel.  Measured on 8 B200 (profiles/
+        // r1_bench_dist8_v2_*.json): S20k 0.593 s pushed vs 0.432 s broadcast, S100k 7.5 s pushed vs 8.4 s
+        // broadcast (there the panel is hidden behind long updates); on 2 GPUs pushing wins (0.539 vs 0.560 s).
+        // p2p_mode: 0 never push, 1 automatic, 2 always push.
+        ctx->push_now = ctx->links.enabled &&
+                        (ctx->p2p_mode == 2 || ctx->world <= 2 || (long)L.NP >= 49152);
+        if (!ctx->push_now) CU(ctx->stage.ensure((size_t)L.MT * ctx->tiles_per_panel * kTile * 8));
     }
     const uint8_t* mask_h = dist ? ctx->col_mask.as<uint8_t>() + L.nxp / kTile : nullptr;
 
