@@ -228,6 +228,10 @@ struct cheq_ctx {
     DeviceBuffer arena, ipc_stage;
     int p2p_mode = 1;                       // CHEQ_DIST_P2P: 0 NCCL broadcasts only, 1 automatic, 2 always push
     bool push_now = false;                  // decision for the current solve
+    bool push_dma = false;                  // push with the copy engines (cudaMemcpy2DAsync to the peers) instead of
+                                            // from the kernels' epilogues
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_leaf = nullptr, ev_copy = nullptr;
     int (*wait_value32)(cudaStream_t, unsigned long long, unsigned, unsigned) = nullptr;
     int (*mem_address_range)(unsigned long long*, size_t*, unsigned long long) = nullptr;
     double ms_comm_host = 0.0;
@@ -523,7 +527,8 @@ struct Dense {
     long strideNeg;
     double flops = 0.0;
     const struct SplitPlan* plan = nullptr;   // wave-aware recursion splits (nullptr: halve)
-    bool push = false;                        // panel outputs are also stored into the peers' memory
+    bool push = false;                        // panel outputs are also stored into the peers' memory (epilogues)
+    bool push_dma = false;                    // each finished tile column is copied to the peers by the copy engines
 };
 
 
@@ -622,6 +627,16 @@ int factor_panel(Dense& D, int j0, int n) {
             }
             const int rc2 = launch_gemm_timed(ctx, g, mt, 1, D.batch, 2.0 * mt * kTile * (double)kTile * kTile);
             if (rc2) return rc2;
+        }
+        if (D.push_dma) {
+            // the finished tile column (diagonal tile + everything below, right-hand-side rows included) goes to
+            // every peer's trapezoid by DMA while this rank carries on with the panel
+            CU(cudaEventRecord(ctx->ev_leaf, ctx->cur));
+            CU(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_leaf, 0));
+            const size_t width = (size_t)(D.MT - j0) * 8;
+            for (int i = 0; i < ctx->links.n; ++i)
+                CU(cudaMemcpy2DAsync((double*)ctx->links.A[i] + (Ajj - D.A), (size_t)D.ld * 8, Ajj, (size_t)D.ld * 8,
+                                     width, kTile, cudaMemcpyDeviceToDevice, ctx->copy_stream));
         }
         const double m = (double)(D.MT - j0 - kTile);
         D.flops += (double)kTile * kTile * kTile / 3.0 + m * kTile * kTile;
@@ -814,7 +829,7 @@ int p2p_setup(cheq_ctx* ctx) {
     cudaStream_t ms = ctx->stream, ps = ctx->panel_stream;
     const int world = ctx->world, rank = ctx->rank;
     if (!lk.tried) {
-        if (const char* env = getenv("CHEQ_DIST_P2P")) ctx->p2p_mode = std::max(0, std::min(2, atoi(env)));
+        if (const char* env = getenv("CHEQ_DIST_P2P")) ctx->p2p_mode = std::max(0, std::min(3, atoi(env)));
         cudaDriverEntryPointQueryResult q;
         void* fn = nullptr;
         if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &fn, cudaEnableDefault, &q) == cudaSuccess &&
@@ -957,9 +972,11 @@ int factor_blocked(Dense& D, int p_begin, int p_end) {
             const SplitPlan* saved = D.plan;
             D.plan = nullptr;   // panels are a few tiles wide: plain halving
             ctx->cur = ps;
-            D.push = push;
+            D.push = push && !ctx->push_dma;
+            D.push_dma = push && ctx->push_dma;
             const int rc = factor_panel(D, j0, n);
             D.push = false;
+            D.push_dma = false;
             ctx->cur = ms;
             D.plan = saved;
             if (rc) return rc;
@@ -970,9 +987,29 @@ int factor_blocked(Dense& D, int p_begin, int p_end) {
             if (mine) {
                 unsigned* words[kMaxPeers];
                 for (int i = 0; i < ctx->links.n; ++i) words[i] = (unsigned*)ctx->links.arena[i] + ctx->rank;
-                LAUNCH(launch_signal_peers(words, ctx->links.n, seq, ps));
                 CU(cudaEventRecord(ctx->ev_bcast, ps));
-                CU(cudaStreamWaitEvent(ms, ctx->ev_bcast, 0));
+                CU(cudaStreamWaitEvent(ms, ctx->ev_bcast, 0));   // this rank's update needs only its own kernels
+                if (ctx->push_dma) {
+                    // the panel's small outputs, then the flag, behind the tile-column copies on the copy stream
+                    cudaStream_t cs = ctx->copy_stream;
+                    CU(cudaStreamWaitEvent(cs, ctx->ev_bcast, 0));
+                    const char* ar = ctx->arena.as<char>();
+                    const double* Lk = D.Linv + (long)(j0 / kTile) * kTile * kTile;
+                    for (int i = 0; i < ctx->links.n; ++i) {
+                        char* pa = ctx->links.arena[i];
+                        CU(cudaMemcpyAsync(pa + ((const char*)Lk - ar), Lk, (size_t)n * kTile * 8,
+                                           cudaMemcpyDeviceToDevice, cs));
+                        CU(cudaMemcpyAsync(pa + ((const char*)(D.sgn + j0) - ar), D.sgn + j0, (size_t)n * 8,
+                                           cudaMemcpyDeviceToDevice, cs));
+                        CU(cudaMemcpyAsync(pa + ((const char*)(D.neg_cnt + j0 / kTile) - ar), D.neg_cnt + j0 / kTile,
+                                           (size_t)(n / kTile) * 4, cudaMemcpyDeviceToDevice, cs));
+                        CU(cudaMemcpyAsync(pa + ((const char*)(D.neg_idx + j0) - ar), D.neg_idx + j0, (size_t)n * 4,
+                                           cudaMemcpyDeviceToDevice, cs));
+                    }
+                    LAUNCH(launch_signal_peers(words, ctx->links.n, seq, cs));
+                } else {
+                    LAUNCH(launch_signal_peers(words, ctx->links.n, seq, ps));
+                }
             } else {
                 const unsigned long long addr = (unsigned long long)(ctx->arena.as<unsigned>() + pp.owner[p]);
                 if (ctx->wait_value32(ms, addr, seq, 0 /* CU_STREAM_WAIT_VALUE_GEQ */) != 0)
@@ -1017,6 +1054,11 @@ int factor_blocked(Dense& D, int p_begin, int p_end) {
         }
         const int rc = update_columns(D, j0, n, e, d_list + pos + head, pp.own_tiles.data() + pos + head, cnt - head);
         if (rc) return rc;
+    }
+    if (ctx->world > 1 && ctx->push_now && ctx->push_dma) {
+        // the copies read this rank's finished panels: nothing later on the main stream may overwrite them first
+        CU(cudaEventRecord(ctx->ev_copy, ctx->copy_stream));
+        CU(cudaStreamWaitEvent(ms, ctx->ev_copy, 0));
     }
     if (ctx->world > 1) {
         // a pivot breakdown seen by one owner must stop every rank
@@ -1320,8 +1362,11 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
         // r1_bench_dist8_v2_*.json): S20k 0.593 s pushed vs 0.432 s broadcast, S100k 7.5 s pushed vs 8.4 s
         // broadcast (there the panel is hidden behind long updates); on 2 GPUs pushing wins (0.539 vs 0.560 s).
         // p2p_mode: 0 never push, 1 automatic, 2 always push.
+        // p2p_mode 3: push with the copy engines (one cudaMemcpy2DAsync per finished tile column and peer, off the
+        // SMs and overlapped with the rest of the panel).
         ctx->push_now = ctx->links.enabled &&
-                        (ctx->p2p_mode == 2 || ctx->world <= 2 || (long)L.NP >= 49152);
+                        (ctx->p2p_mode >= 2 || ctx->world <= 2 || (long)L.NP >= 49152);
+        ctx->push_dma = ctx->push_now && ctx->p2p_mode == 3;
         if (!ctx->push_now) CU(ctx->stage.ensure((size_t)L.MT * ctx->tiles_per_panel * kTile * 8));
     }
     const uint8_t* mask_h = dist ? ctx->col_mask.as<uint8_t>() + L.nxp / kTile : nullptr;
@@ -1651,7 +1696,10 @@ int32_t cheq_ctx_create(int32_t device, cheq_ctx** out) {
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaStreamCreateWithPriority(&ctx->panel_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&ctx->ev_bcast, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&ctx->ev_bcast, cudaEventDisableTiming) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_leaf, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return CHEQ_ERR_CUDA;
     }
@@ -1674,6 +1722,10 @@ void cheq_ctx_destroy(cheq_ctx* ctx) {
     p2p_close(ctx);
     ctx->arena.release();
     ctx->ipc_stage.release();
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+    if (ctx->ev_leaf) cudaEventDestroy(ctx->ev_leaf);
+    if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->ev_ready) cudaEventDestroy(ctx->ev_ready);
     if (ctx->ev_bcast) cudaEventDestroy(ctx->ev_bcast);
     if (ctx->panel_stream) cudaStreamDestroy(ctx->panel_stream);
