@@ -232,6 +232,9 @@ struct cheq_ctx {
                                             // from the kernels' epilogues
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_leaf = nullptr, ev_copy = nullptr;
+    cudaStream_t bulk_stream = nullptr;     // below-the-panel work of the tile-level look-ahead
+    cudaEvent_t ev_c[64] = {}, ev_b[64] = {};
+    int panel_flat = 1;                     // CHEQ_PANEL_FLAT=0: recursive kernel sequence inside a panel
     int (*wait_value32)(cudaStream_t, unsigned long long, unsigned, unsigned) = nullptr;
     int (*mem_address_range)(unsigned long long*, size_t*, unsigned long long) = nullptr;
     double ms_comm_host = 0.0;
@@ -674,6 +677,147 @@ int factor_panel(Dense& D, int j0, int n) {
     return factor_panel(D, j0 + n1, n - n1);
 }
 
+// Panel factorisation with TILE-LEVEL look-ahead (blocked schedule).  The dependency chain of a panel of T tile
+// columns is  potrf(t) -> in-panel solve (tiles t+1..T-1 of column t) -> in-panel update -> potrf(t+1): these run
+// on the panel stream.  Everything below the panel -- the update of column t by the panel's earlier columns and its
+// triangular solve -- runs on the bulk stream one tile column behind, concurrently with the next potrf.
+int factor_panel_flat(Dense& D, int j0, int n) {
+    cheq_ctx* ctx = D.ctx;
+    const int T = n / kTile;
+    cudaStream_t ps = ctx->panel_stream, bs = ctx->bulk_stream;
+    const int rb = j0 + n;                      // first row below the panel
+    const int mb = (D.MT - rb) / kTile;         // tile rows below it (>= 1: the right-hand-side rows)
+    const double tile3 = (double)kTile * kTile * kTile;
+    auto peers_of = [&](GemmArgs& g) {
+        if (!D.push) return;
+        g.n_peers = ctx->links.n;
+        for (int i = 0; i < g.n_peers; ++i) g.peerC[i] = (double*)ctx->links.A[i] + (g.C - D.A);
+    };
+    for (int t = 0; t < T; ++t) {
+        const int jt = j0 + t * kTile;
+        double* Ajj = D.A + (long)jt + (long)jt * D.ld;
+        double* Lk = D.Linv + (long)(jt / kTile) * kTile * kTile;
+        // ---- chain (panel stream) ----
+        ctx->cur = ps;
+        if (int rcp = prof_begin(ctx, 1)) return rcp;
+        PotrfPeers pp{};
+        if (D.push) {
+            const cheq_ctx::PeerLinks& lk = ctx->links;
+            pp.n = lk.n;
+            for (int i = 0; i < lk.n; ++i) {
+                pp.A[i] = (double*)lk.A[i] + (Ajj - D.A);
+                pp.Minv[i] = (double*)(lk.arena[i] + ((char*)Lk - ctx->arena.as<char>()));
+                pp.sgn[i] = (double*)(lk.arena[i] + ((char*)(D.sgn + jt) - ctx->arena.as<char>()));
+                pp.neg_cnt[i] = (int*)(lk.arena[i] + ((char*)(D.neg_cnt + jt / kTile) - ctx->arena.as<char>()));
+                pp.neg_idx[i] = (int*)(lk.arena[i] + ((char*)(D.neg_idx + (long)jt) - ctx->arena.as<char>()));
+            }
+        }
+        LAUNCH(launch_potrf_tile(Ajj, D.ld, D.strideA, Lk, D.strideLinv, D.sgn + jt, D.strideSgn, D.neg_cnt + jt / kTile,
+                                 D.neg_idx + (long)jt, D.strideNeg, D.state, kPivotTol, D.batch, ps,
+                                 D.push ? &pp : nullptr));
+        if (int rcp = prof_end(ctx)) return rcp;
+        D.flops += tile3 / 3.0;
+        const int mt_in = T - 1 - t;            // tiles of this column that lie inside the panel, below the diagonal
+        if (mt_in > 0) {
+            GemmArgs g{};                       // in-panel solve: L[t+1.., t] = A[t+1.., t] M_t^T
+            g.A = Ajj + kTile;
+            g.lda = D.ld;
+            g.strideA = D.strideA;
+            g.B = Lk;
+            g.ldb = kTile;
+            g.strideB = D.strideLinv;
+            g.C = Ajj + kTile;
+            g.ldc = D.ld;
+            g.strideC = D.strideA;
+            g.K = kTile;
+            g.state = D.state;
+            peers_of(g);
+            int rc = launch_gemm_timed(ctx, g, mt_in, 1, D.batch, 2.0 * mt_in * tile3);
+            if (rc) return rc;
+            GemmArgs u{};                       // in-panel update of the tiles right of column t
+            u.A = Ajj + kTile;
+            u.lda = D.ld;
+            u.strideA = D.strideA;
+            u.B = u.A;
+            u.ldb = D.ld;
+            u.strideB = D.strideA;
+            u.C = D.A + (long)(jt + kTile) + (long)(jt + kTile) * D.ld;
+            u.ldc = D.ld;
+            u.strideC = D.strideA;
+            u.K = kTile;
+            u.lower = 1;
+            u.subtract = 1;
+            u.neg_cnt = D.neg_cnt + jt / kTile;
+            u.neg_idx = D.neg_idx + (long)jt;
+            u.strideNeg = D.strideNeg;
+            u.state = D.state;
+            const double fu = tile3 * mt_in * (double)mt_in;
+            rc = launch_gemm_timed(ctx, u, mt_in, mt_in, D.batch, fu);
+            if (rc) return rc;
+            D.flops += mt_in * tile3 + fu;
+        }
+        CU(cudaEventRecord(ctx->ev_c[t], ps));
+        // ---- below the panel (bulk stream) ----
+        CU(cudaStreamWaitEvent(bs, ctx->ev_c[t], 0));
+        ctx->cur = bs;
+        if (t > 0) {
+            GemmArgs r{};                       // A[below, t] -= sum_{t' < t} L[below, t'] S L[t, t']^T
+            r.A = D.A + (long)rb + (long)j0 * D.ld;
+            r.lda = D.ld;
+            r.strideA = D.strideA;
+            r.B = D.A + (long)jt + (long)j0 * D.ld;
+            r.ldb = D.ld;
+            r.strideB = D.strideA;
+            r.C = D.A + (long)rb + (long)jt * D.ld;
+            r.ldc = D.ld;
+            r.strideC = D.strideA;
+            r.K = t * kTile;
+            r.subtract = 1;
+            r.neg_cnt = D.neg_cnt + j0 / kTile;
+            r.neg_idx = D.neg_idx + (long)j0;
+            r.strideNeg = D.strideNeg;
+            r.state = D.state;
+            const double fr = 2.0 * mb * t * tile3;
+            const int rc = launch_gemm_timed(ctx, r, mb, 1, D.batch, fr);
+            if (rc) return rc;
+            D.flops += fr;
+        }
+        {
+            GemmArgs l{};                       // L[below, t] = A[below, t] M_t^T
+            l.A = D.A + (long)rb + (long)jt * D.ld;
+            l.lda = D.ld;
+            l.strideA = D.strideA;
+            l.B = Lk;
+            l.ldb = kTile;
+            l.strideB = D.strideLinv;
+            l.C = D.A + (long)rb + (long)jt * D.ld;
+            l.ldc = D.ld;
+            l.strideC = D.strideA;
+            l.K = kTile;
+            l.state = D.state;
+            peers_of(l);
+            const int rc = launch_gemm_timed(ctx, l, mb, 1, D.batch, 2.0 * mb * tile3);
+            if (rc) return rc;
+            D.flops += mb * tile3;
+        }
+        CU(cudaEventRecord(ctx->ev_b[t], bs));
+        if (D.push_dma) {
+            // column t is final in both parts: DMA it to the peers while the panel goes on
+            cudaStream_t cs = ctx->copy_stream;
+            CU(cudaStreamWaitEvent(cs, ctx->ev_c[t], 0));
+            CU(cudaStreamWaitEvent(cs, ctx->ev_b[t], 0));
+            const size_t width = (size_t)(D.MT - jt) * 8;
+            for (int i = 0; i < ctx->links.n; ++i)
+                CU(cudaMemcpy2DAsync((double*)ctx->links.A[i] + (Ajj - D.A), (size_t)D.ld * 8, Ajj, (size_t)D.ld * 8,
+                                     width, kTile, cudaMemcpyDeviceToDevice, cs));
+        }
+    }
+    // "panel stream done" must mean that the whole panel is done
+    CU(cudaStreamWaitEvent(ps, ctx->ev_b[T - 1], 0));
+    ctx->cur = ps;
+    return CHEQ_OK;
+}
+
 // Schur update of the trailing block by an already factored leading block [0, k): C[k:MT, k:NP] -= W W^T.
 int schur_update(Dense& D, int k, int ncols) {
     cheq_ctx* ctx = D.ctx;
@@ -974,7 +1118,13 @@ int factor_blocked(Dense& D, int p_begin, int p_end) {
             ctx->cur = ps;
             D.push = push && !ctx->push_dma;
             D.push_dma = push && ctx->push_dma;
-            const int rc = factor_panel(D, j0, n);
+            // the bulk stream starts from what the panel stream sees now (all earlier updates of these columns)
+            if (ctx->panel_flat && D.batch == 1 && n / kTile <= 64) {
+                CU(cudaEventRecord(ctx->ev_leaf, ps));
+                CU(cudaStreamWaitEvent(ctx->bulk_stream, ctx->ev_leaf, 0));
+            }
+            const int rc = (ctx->panel_flat && D.batch == 1 && n / kTile <= 64) ? factor_panel_flat(D, j0, n)
+                                                                                  : factor_panel(D, j0, n);
             D.push = false;
             D.push_dma = false;
             ctx->cur = ms;
@@ -1357,16 +1507,16 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
         D.neg_idx = (int*)(ar + AL.neg_idx);
         rc = p2p_setup(ctx);   // start-of-solve barrier + peer mappings
         if (rc) return rc;
-        // Data plane for this solve.  Pushing from the epilogues costs (world - 1) unicast copies of every panel on
-        // the owner's critical path; a broadcast costs one copy after the panel.  Measured on 8 B200 (profiles/
-        // r1_bench_dist8_v2_*.json): S20k 0.593 s pushed vs 0.432 s broadcast, S100k 7.5 s pushed vs 8.4 s
-        // broadcast (there the panel is hidden behind long updates); on 2 GPUs pushing wins (0.539 vs 0.560 s).
-        // p2p_mode: 0 never push, 1 automatic, 2 always push.
-        // p2p_mode 3: push with the copy engines (one cudaMemcpy2DAsync per finished tile column and peer, off the
-        // SMs and overlapped with the rest of the panel).
-        ctx->push_now = ctx->links.enabled &&
-                        (ctx->p2p_mode >= 2 || ctx->world <= 2 || (long)L.NP >= 49152);
-        ctx->push_dma = ctx->push_now && ctx->p2p_mode == 3;
+        // Data plane for this solve (CHEQ_DIST_P2P: 0 broadcast, 1 automatic, 2 push from the kernels' epilogues,
+        // 3 push with the copy engines).  Measured on B200 (profiles/r1_bench_dist*_v[23]_*.json, r1_s100k_*):
+        //   S20k, 2 GPUs: DMA push 0.510 s < epilogue push 0.537 < NCCL broadcast 0.560
+        //   S20k, 8 GPUs: NCCL broadcast 0.432 s < DMA push 0.491 < epilogue push 0.593  (7 unicast copies of every
+        //                 panel cost more than one broadcast when the panel is on the critical path)
+        //   S100k, 8 GPUs: DMA push 6.92 s (24.4 TF/s per GPU) < epilogue push 7.52 < NCCL broadcast 8.38
+        //                 (the panel is hidden behind long updates; pushing removes pack / broadcast / unpack)
+        const bool want_push = ctx->p2p_mode >= 2 || (ctx->p2p_mode == 1 && (ctx->world <= 2 || (long)L.NP >= 49152));
+        ctx->push_now = ctx->links.enabled && want_push;
+        ctx->push_dma = ctx->push_now && ctx->p2p_mode != 2;
         if (!ctx->push_now) CU(ctx->stage.ensure((size_t)L.MT * ctx->tiles_per_panel * kTile * 8));
     }
     const uint8_t* mask_h = dist ? ctx->col_mask.as<uint8_t>() + L.nxp / kTile : nullptr;
@@ -1698,11 +1848,19 @@ int32_t cheq_ctx_create(int32_t device, cheq_ctx** out) {
         cudaEventCreateWithFlags(&ctx->ev_ready, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_bcast, cudaEventDisableTiming) != cudaSuccess ||
         cudaStreamCreateWithPriority(&ctx->copy_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&ctx->bulk_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_leaf, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_copy, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
         return CHEQ_ERR_CUDA;
     }
+    for (int i = 0; i < 64; ++i)
+        if (cudaEventCreateWithFlags(&ctx->ev_c[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ctx->ev_b[i], cudaEventDisableTiming) != cudaSuccess) {
+            delete ctx;
+            return CHEQ_ERR_CUDA;
+        }
+    if (const char* env = getenv("CHEQ_PANEL_FLAT")) ctx->panel_flat = atoi(env) != 0;
     if (const char* env = getenv("CHEQ_FACTOR_MODE")) ctx->factor_mode = atoi(env) == 1 ? 1 : 0;
     if (const char* env = getenv("CHEQ_TILES_PER_PANEL")) ctx->tiles_per_panel = std::max(1, std::min(64, atoi(env)));
     *out = ctx;
@@ -1722,6 +1880,14 @@ void cheq_ctx_destroy(cheq_ctx* ctx) {
     p2p_close(ctx);
     ctx->arena.release();
     ctx->ipc_stage.release();
+    if (ctx->bulk_stream) {
+        cudaStreamSynchronize(ctx->bulk_stream);
+        cudaStreamDestroy(ctx->bulk_stream);
+    }
+    for (int i = 0; i < 64; ++i) {
+        if (ctx->ev_c[i]) cudaEventDestroy(ctx->ev_c[i]);
+        if (ctx->ev_b[i]) cudaEventDestroy(ctx->ev_b[i]);
+    }
     if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     if (ctx->ev_leaf) cudaEventDestroy(ctx->ev_leaf);
     if (ctx->ev_copy) cudaEventDestroy(ctx->ev_copy);
