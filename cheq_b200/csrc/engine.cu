@@ -1514,7 +1514,8 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
         //                 panel cost more than one broadcast when the panel is on the critical path)
         //   S100k, 8 GPUs: DMA push 6.92 s (24.4 TF/s per GPU) < epilogue push 7.52 < NCCL broadcast 8.38
         //                 (the panel is hidden behind long updates; pushing removes pack / broadcast / unpack)
-        const bool want_push = ctx->p2p_mode >= 2 || (ctx->p2p_mode == 1 && (ctx->world <= 2 || (long)L.NP >= 49152));
+        //   S20k, 4 GPUs: DMA push 0.455 s < NCCL broadcast 0.466
+        const bool want_push = ctx->p2p_mode >= 2 || (ctx->p2p_mode == 1 && (ctx->world <= 4 || (long)L.NP >= 49152));
         ctx->push_now = ctx->links.enabled && want_push;
         ctx->push_dma = ctx->push_now && ctx->p2p_mode != 2;
         if (!ctx->push_now) CU(ctx->stage.ensure((size_t)L.MT * ctx->tiles_per_panel * kTile * 8));
