@@ -437,8 +437,10 @@ def run_ours(args, rank, local_rank, world):
                                f"({iterations} iterations), total charge 0, default SolverOptions",
                    "parallelism": (f"one system over {world} GPUs: 1-D block-cyclic column panels ("
                                    f"{os.environ.get('CHEQ_TILES_PER_PANEL', '4')} x 128 columns), owner-computes "
-                                   "assembly/updates, NCCL panel broadcast with one-panel look-ahead, replicated "
-                                   "triangular solves") if world > 1 else "single GPU",
+                                   "assembly/updates, finished panels pushed to the peers over NVLink (copy engines, "
+                                   "CUDA IPC mappings, flag + cuStreamWaitValue32) up to 4 GPUs or NCCL-broadcast "
+                                   "beyond, panel- and tile-level look-ahead, replicated triangular solves "
+                                   f"(CHEQ_DIST_P2P={os.environ.get('CHEQ_DIST_P2P', '1')})") if world > 1 else "single GPU",
                    "l2": "working set (3.3 GB matrix) >> 126 MB L2; no flush needed",
                    "phases_ms": {k: stats[k] for k in ("ms_host_prepare", "ms_h2d", "ms_assemble", "ms_factor_once",
                                                        "ms_scf", "ms_d2h")},
