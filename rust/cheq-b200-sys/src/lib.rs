@@ -58,4 +58,20 @@ extern "C" {
         options: *const cheq_options, charges_out: *mut f64, potential_out: *mut f64,
         iterations_out: *mut u32, delta_out: *mut f64, status_out: *mut i32,
     ) -> i32;
+
+    // ---- one dense system over the GPUs of a node (one process per GPU; include/cheq_b200.h) ----
+    /// Rank 0: fills 128 bytes that every rank must receive (any transport) before `cheq_ctx_dist_init`.
+    pub fn cheq_dist_unique_id(id_out: *mut u8) -> i32;
+    /// Joins the group; afterwards single-frame solves on `ctx` are collective (same inputs on every rank).
+    pub fn cheq_ctx_dist_init(ctx: *mut cheq_ctx, rank: i32, world: i32, id: *const u8) -> i32;
+    pub fn cheq_ctx_dist_info(ctx: *const cheq_ctx, rank_out: *mut i32, world_out: *mut i32) -> i32;
+    /// 0 = automatic schedule, 1 = right-looking panels with look-ahead also on one GPU.
+    pub fn cheq_set_factor_mode(ctx: *mut cheq_ctx, mode: i32, tiles_per_panel: i32) -> i32;
+    /// Host-only: owner rank and panel index of every 128-column tile.
+    pub fn cheq_dist_plan(
+        x_tiles: i32, h_tiles: i32, tiles_per_panel: i32, world: i32, tile_owner_out: *mut i32,
+        tile_panel_out: *mut i32,
+    ) -> i32;
 }
+
+pub const CHEQ_DIST_ID_BYTES: usize = 128;

@@ -195,3 +195,37 @@ def test_workload_generators_are_seeded_and_physical():
     assert len(Zo) == 200 and set(Zo) <= {1, 6, 7, 8}
     fr = W.md_frames(xo, 3)
     assert fr.shape == (3, 200, 3) and not np.array_equal(fr[0], fr[1])
+
+
+# ---- multi-GPU entry points: argument checking needs no GPU ----------------------------------------------------
+def test_dist_entry_points_reject_bad_arguments_without_gpu():
+    lib = _ffi.lib()
+    assert lib.cheq_ctx_dist_init(None, 0, 2, None) == _ffi.INVALID_ARGUMENT
+    assert lib.cheq_ctx_dist_info(None, None, None) == _ffi.INVALID_ARGUMENT
+    assert lib.cheq_set_factor_mode(None, 0, 4) == _ffi.INVALID_ARGUMENT
+    assert lib.cheq_dist_unique_id(None) == _ffi.INVALID_ARGUMENT
+    assert lib.cheq_dbg_potrf_cycles(None, None, 0) == _ffi.INVALID_ARGUMENT
+    owner = np.zeros(5, dtype=np.int32)
+    assert lib.cheq_dist_plan(2, 3, 2, 3, owner.ctypes.data_as(C.c_void_p), None) == _ffi.OK
+    assert owner.tolist() == [0, 0, 1, 1, 2]       # X block: one 2-tile panel; H block: panels of 2 + 1 tiles
+
+
+def test_join_without_process_group_is_a_no_op():
+    """cheq_b200.distributed.join leaves a context alone when torch.distributed is not initialised (single GPU)."""
+    from cheq_b200 import distributed
+
+    class FakeCtx:
+        pass
+    distributed.join(FakeCtx())                    # must not touch the context
+
+
+def test_s100k_generator_is_seeded_and_physical():
+    from scipy.spatial import cKDTree
+
+    from cheq_b200 import workloads as W
+    Z, xyz = W.solvated_100k(n_solute=400, n_waters=1200)
+    Z2, xyz2 = W.solvated_100k(n_solute=400, n_waters=1200)
+    assert Z == Z2 and np.array_equal(xyz, xyz2) and len(Z) == 400 + 3 * 1200
+    assert Z[400:403] == [8, 1, 1] and set(Z[:400]) <= {1, 6, 7, 8}
+    d, _ = cKDTree(xyz).query(xyz, k=2)
+    assert d[:, 1].min() > 0.9                      # SURVEY.md section 8(d): minimum inter-atomic distance
