@@ -1268,8 +1268,15 @@ struct Prepared {
     int batch = 1;
 };
 
-bool use_blocked(const cheq_ctx* ctx, int batch) {
-    return batch == 1 && (ctx->world > 1 || ctx->factor_mode == 1);
+// Which factorisation schedule a solve uses.  Right-looking panels with look-ahead are required for a group.  On
+// one GPU they were measured 1.3 % faster than the recursive schedule for S20k (0.754 vs 0.764 s, profiles/
+// r1_bench_v3*.json) but run the dominant GEMM at K = 512 (21 instead of 28 TFLOP/s) and lose beyond ~40k rows,
+// so the recursive kernel sequence stays the single-GPU default; mode 1 selects panels explicitly.
+// CHEQ_FACTOR_MODE / cheq_set_factor_mode: 0 automatic, 1 always panels, 2 never panels on one GPU.
+bool use_blocked(const cheq_ctx* ctx, int batch, long NP) {
+    (void)NP;
+    if (batch != 1) return false;
+    return ctx->world > 1 || ctx->factor_mode == 1;
 }
 
 int prepare_and_assemble(cheq_ctx* ctx, const SolveIO& io, long frame0, int batch, bool hydrogen_scf,
@@ -1461,7 +1468,7 @@ int prepare_and_assemble(cheq_ctx* ctx, const SolveIO& io, long frame0, int batc
     aa.pos_stride = L.NP;
     aa.NP = L.NP;
     aa.rcut2_max = P.rcut2_max;
-    if (use_blocked(ctx, batch)) {
+    if (use_blocked(ctx, batch, L.NP)) {
         // distributed assembly: every rank produces only the tile columns it owns
         rc = ensure_panel_plan(ctx, L);
         if (rc) return rc;
@@ -1491,7 +1498,7 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
     double* xs = ctx->xsol.as<double>();
     double* q = ctx->q.as<double>();
     int rc;
-    const bool blocked = use_blocked(ctx, batch);
+    const bool blocked = use_blocked(ctx, batch, L.NP);
     const bool dist = blocked && ctx->world > 1;
     const PanelPlan& pp = ctx->pplan;
     if (dist) {
@@ -1862,7 +1869,7 @@ int32_t cheq_ctx_create(int32_t device, cheq_ctx** out) {
             return CHEQ_ERR_CUDA;
         }
     if (const char* env = getenv("CHEQ_PANEL_FLAT")) ctx->panel_flat = atoi(env) != 0;
-    if (const char* env = getenv("CHEQ_FACTOR_MODE")) ctx->factor_mode = atoi(env) == 1 ? 1 : 0;
+    if (const char* env = getenv("CHEQ_FACTOR_MODE")) ctx->factor_mode = std::max(0, std::min(2, atoi(env)));
     if (const char* env = getenv("CHEQ_TILES_PER_PANEL")) ctx->tiles_per_panel = std::max(1, std::min(64, atoi(env)));
     *out = ctx;
     return CHEQ_OK;
@@ -1981,7 +1988,7 @@ int32_t cheq_ctx_dist_info(const cheq_ctx* ctx, int32_t* rank_out, int32_t* worl
 }
 
 int32_t cheq_set_factor_mode(cheq_ctx* ctx, int32_t mode, int32_t tiles_per_panel) {
-    if (!ctx || mode < 0 || mode > 1 || tiles_per_panel < 0 || tiles_per_panel > 64) return CHEQ_ERR_INVALID_ARGUMENT;
+    if (!ctx || mode < 0 || mode > 2 || tiles_per_panel < 0 || tiles_per_panel > 64) return CHEQ_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(ctx->mu);
     ctx->factor_mode = mode;
     if (tiles_per_panel > 0) ctx->tiles_per_panel = tiles_per_panel;

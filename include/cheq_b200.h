@@ -115,8 +115,8 @@ int32_t cheq_set_profiling(cheq_ctx* ctx, int32_t enabled);
 int32_t cheq_dist_unique_id(uint8_t* id_out /* CHEQ_DIST_ID_BYTES */);
 int32_t cheq_ctx_dist_init(cheq_ctx* ctx, int32_t rank, int32_t world, const uint8_t* id);
 int32_t cheq_ctx_dist_info(const cheq_ctx* ctx, int32_t* rank_out, int32_t* world_out);
-/* Factorisation schedule: mode 0 = automatic (recursive tall-panel on one GPU, right-looking panels with
- * look-ahead when the context is part of a group), 1 = right-looking panels with look-ahead also on one GPU.
+/* Factorisation schedule: mode 0 = automatic (right-looking panels with look-ahead when the context is part of a
+ * group, the recursive tall-panel sequence on one GPU), 1 = always panels, 2 = never panels on one GPU.
  * tiles_per_panel: panel width in 128-column tiles (0 keeps the current value; default 4). */
 int32_t cheq_set_factor_mode(cheq_ctx* ctx, int32_t mode, int32_t tiles_per_panel);
 /* Host-only: the owner rank and panel index of every 128-column tile for a layout with x_tiles non-hydrogen and
