@@ -453,6 +453,10 @@ def run_ours(args, rank, local_rank, world):
                      "measured_in": f"second pass of {args.steps} steps with per-launch CUDA events "
                                     f"({ms_profiled / args.steps:.1f} ms per step vs {ms_total / args.steps:.1f} uninstrumented)",
                      "potrf_ms_per_step": stats["potrf_ms"], "backsolve_ms_per_step": stats["backsolve_ms"],
+                     "note": ("panel schedule: GEMMs of the main, panel and bulk streams run concurrently, so the "
+                              "summed per-launch durations overstate the kernel's wall-clock share and understate "
+                              "its rate" if (world > 1 or os.environ.get("CHEQ_FACTOR_MODE") == "1") else
+                              "recursive schedule: one stream, launches do not overlap"),
                      "peak_source": f"cuBLAS DGEMM 8192^3 measured in this run: sustained {peak_sustained:.1f}, "
                                     f"burst {peak_burst:.1f} TFLOP/s (MEASURED_PEAKS.json has no fp64 entry)"},
         "roofline_assembly": {"bound": "hbm", "kernel": "assemble_lower_kernel<STO>", "achieved": asm_gbs,
