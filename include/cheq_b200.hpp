@@ -285,6 +285,21 @@ class QEqSolver {
     }
     const SolverOptions& options() const { return options_; }
 
+    // ---- one dense system over the GPUs of a node (no reference equivalent; include/cheq_b200.h) ----
+    // Rank 0 creates the id, the caller ships the 128 bytes to every rank (MPI_Bcast, a file, ...), every rank
+    // joins with its own solver; afterwards solve / solve_in_field are collective.
+    static std::array<uint8_t, CHEQ_DIST_ID_BYTES> dist_unique_id() {
+        std::array<uint8_t, CHEQ_DIST_ID_BYTES> id{};
+        if (cheq_dist_unique_id(id.data()) != CHEQ_OK)
+            throw CheqError(CheqError::Kind::Cuda, "cheq_dist_unique_id failed (NCCL not loadable)");
+        return id;
+    }
+    void join_group(int rank, int world, const std::array<uint8_t, CHEQ_DIST_ID_BYTES>& id, int device) {
+        ensure_ctx(device);
+        if (cheq_ctx_dist_init(ctx_.get(), rank, world, id.data()) != CHEQ_OK)
+            throw CheqError(CheqError::Kind::Cuda, std::string("cheq_ctx_dist_init: ") + cheq_last_error(ctx_.get()));
+    }
+
     template <class A>
     CalculationResult solve(const std::vector<A>& atoms, double total_charge, int device = 0) {   // :174-188
         return solve_impl(atoms, total_charge, nullptr, device);

@@ -1,0 +1,53 @@
+"""The bench.py output contract, checked on the committed B200 lines (profiles/) so that a CPU-only run notices a
+key that went missing: one JSON object per run with the driver's keys, the roofline / cpu_baseline / e2e blocks of
+the task contract, and the multi-GPU lines of the same metric."""
+import json
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+             "vs_baseline", "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks"}
+
+
+def _line(name):
+    txt = (ROOT / "profiles" / name).read_text().strip().splitlines()
+    return json.loads([l for l in txt if l.startswith("{")][-1])
+
+
+def test_single_gpu_line_has_the_contract_keys():
+    d = _line("r1_bench_v3.json")
+    assert BASE_KEYS <= set(d), BASE_KEYS - set(d)
+    assert d["metric"] == "qeq_solve_time_n20k_sto_fp64" and d["unit"] == "s" and d["higher_is_better"] is False
+    assert d["n_gpus"] == 1 and d["dtype"] == "f64" and d["data"] == "synthetic" and d["warmup"] >= 3
+    assert "workload" in d["config"] and "S20k" in d["config"]["workload"] and "model" not in d["config"]
+    r = d["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(r) and r["bound"] == "tensor"
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.5 < r["frac"] < 1.0
+    c = d["cpu_baseline"]
+    assert {"value", "unit", "cores", "kind", "sample"} <= set(c) and c["kind"] == "port" and c["cores"] >= 1
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["unit"] == "s"
+    assert d["gpu_launches"] > 0
+    assert not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert d["value"] < 1.0                        # north_star: well under a second on one B200
+    assert c["value"] / d["e2e"]["value"] > 50     # reported beside the CPU path, not the target
+
+
+def test_reference_arm_line():
+    d = _line("r1_bench_v3_reference_arm.json")
+    assert d["impl"] == "reference" and d["metric"] == "qeq_solve_time_n20k_sto_fp64"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["value"] == d["value"] and d["gpu_launches"] == 0
+
+
+@pytest.mark.parametrize("name, gpus", [("r1_bench_dist2_v4_final.json", 2), ("r1_bench_dist4_v3_dma_flat.json", 4),
+                                        ("r1_bench_dist8_v4_final.json", 8)])
+def test_multi_gpu_lines_are_strong_scaling_of_the_same_metric(name, gpus):
+    d = _line(name)
+    one = _line("r1_bench_v3.json")
+    assert BASE_KEYS <= set(d)
+    assert d["n_gpus"] == gpus and d["scaling"] == "strong" and d["metric"] == one["metric"]
+    assert d["config"]["workload"] == one["config"]["workload"]          # the SAME system, solved together
+    assert d["value"] < one["value"]                                     # and faster than on one GPU
