@@ -587,6 +587,238 @@ potrf_tile_pipe_kernel(double* A_, long lda, long strideA, double* Minv_, long s
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// Diagonal tile with a dedicated CHAIN WARP (experimental, CHEQ_POTRF_CW=1).  Same arithmetic and outputs as potrf_tile_kernel.
+//
+// In the rank-1 kernel the thread that owns the pivot spends 505 cycles per step on the dependency chain (pivot ->
+// rsqrt -> column scaling -> publish) and then 433 cycles on its share of the rank-1 update, while the other seven
+// warps wait at the barrier (profiles/r1_potrf_variants.txt).  Here the chain runs in a ninth warp:
+//   update warps (8 x 32 threads, the tile in registers as before), step k:
+//     the 16 owners of column k+1 first apply update k to that column and publish it raw (colbuf), their warp
+//     arrives at a named barrier; then every warp does the rest of update k; __syncthreads.
+//   chain warp, step k: waits on the named barrier, turns the raw column k+1 into the scaled column u (ubuf) and
+//     the final column values (keepbuf: L below the pivot, X = L^-1 above it), records pivot sign and inverse;
+//     __syncthreads.  The owners pick their final column up from keepbuf at the start of the next step.
+// Step time: max(chain, update) instead of chain + update.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kCwThreads = kPotrfThreads + 32;
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void cw_chain_step(int kp, int lane, const double* col, double* u_out, double* keep_out,
+                                              double* dinv, double* sg, ScfState* state, int frame,
+                                              double pivot_tol) {
+    double v[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) v[m] = col[lane + 32 * m];
+    const double d = col[kp];
+    const double ad = fabs(d);
+    const bool bad = !(ad > pivot_tol) || !(ad < 1.0e30);
+    const double sgnk = (d < 0.0) ? -1.0 : 1.0;
+    double il = rsqrt_pivot(ad);
+    double l = ad * il;
+    {
+        const double res = fma(-l, l, ad);
+        l = fma(0.5 * il, res, l);
+        il = fma(fma(-l, il, 1.0), il, il);
+    }
+    il = bad ? 1.0 : il;
+    l = bad ? 1.0 : l;
+    const double sil = sgnk * il;
+    if (lane == 0) {
+        dinv[kp] = il;
+        sg[kp] = sgnk;
+        if (bad && state) atomicExch(&state[frame].info, kp + 1);
+    }
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+        const int r = lane + 32 * m;
+        double u = v[m] * sil, keep = (r > kp) ? u : v[m] * il;
+        if (r == kp) {
+            u = sil;
+            keep = l;
+        }
+        u_out[r] = u;
+        keep_out[r] = keep;
+    }
+}
+
+template <int KB>
+__device__ __forceinline__ void potrf_cw_block(double (&e)[8][8], int ty, int tx, bool p_diag, int& cur,
+                                               double (*ubuf)[kTile], double (*colbuf)[kTile],
+                                               double (*keepbuf)[kTile], const double* sg) {
+    constexpr int kb = KB;
+    constexpr int bn = (KB < 7) ? KB + 1 : 7;
+    for (int kt = 0; kt < 16; ++kt) {
+        const int k = kb * 16 + kt;
+        if (tx == kt) {   // my column k is final: take it back from the chain warp
+#pragma unroll
+            for (int a = 0; a < 8; ++a) e[a][kb] = keepbuf[cur][ty + 16 * a];
+        }
+        const double sk = sg[k];
+        const bool p_row = ty <= kt;    // rows of block kb that are <= k
+        const bool p_col = tx > kt;     // columns of block kb that are > k
+        double su[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) su[a] = sk * ubuf[cur][ty + 16 * a];
+        // ---- owners of column k + 1: bring it up to date, hand it to the chain warp ----
+        bool done_same = false, done_next = false;
+        if (kt < 15) {
+            if (tx == kt + 1) {
+                const double uc = ubuf[cur][tx + 16 * kb];
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    if (POTRF_UPD(a, kb, kb)) e[a][kb] = fma(-su[a], uc, e[a][kb]);
+                    colbuf[cur ^ 1][ty + 16 * a] = e[a][kb];
+                }
+                done_same = true;
+            }
+            if ((tx >> 1) == ((kt + 1) >> 1)) named_bar_arrive(1, 64);   // the warp that contains those owners
+        } else if (KB < 7) {
+            if (tx == 0) {
+                const double uc = ubuf[cur][tx + 16 * bn];
+#pragma unroll
+                for (int a = 0; a < 8; ++a) {
+                    if (POTRF_UPD(a, bn, kb)) e[a][bn] = fma(-su[a], uc, e[a][bn]);
+                    colbuf[cur ^ 1][ty + 16 * a] = e[a][bn];
+                }
+                done_next = true;
+            }
+            if ((tx >> 1) == 0) named_bar_arrive(1, 64);
+        }
+        // ---- everybody: the rest of update k ----
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            if (b < kb) continue;                 // columns <= k: finished
+            if (b == kb && (!p_col || done_same)) continue;
+            if (b == bn && KB < 7 && done_next) continue;
+            const double uc = ubuf[cur][tx + 16 * b];
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+                if (POTRF_UPD(a, b, kb)) e[a][b] = fma(-su[a], uc, e[a][b]);
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+}
+
+__global__ void __launch_bounds__(kCwThreads)
+potrf_tile_cw_kernel(double* A_, long lda, long strideA, double* Minv_, long strideM, double* sgn_, long strideSgn,
+                     int* neg_cnt_, int* neg_idx_, long strideNeg, ScfState* state, double pivot_tol) {
+    const int frame = blockIdx.z;
+    if (state && !state[frame].active) return;
+    extern __shared__ __align__(16) double Ms[];   // staging of M for a coalesced store
+    __shared__ double ubuf[2][kTile], colbuf[2][kTile], keepbuf[2][kTile];
+    __shared__ double dinv[kTile];
+    __shared__ double sg[kTile];
+    double* A = A_ + (long)frame * strideA;
+    double* Minv = Minv_ + (long)frame * strideM;
+    const int t = threadIdx.x;
+    const int ty = t & 15, tx = t >> 4;            // tx == 16, 17: the chain warp
+
+    if (t >= kPotrfThreads) {
+        // ---------------- chain warp ----------------
+        const int lane = t & 31;
+        int cur = 0;
+        named_bar_sync(1, 64);
+        cw_chain_step(0, lane, colbuf[0], ubuf[0], keepbuf[0], dinv, sg, state, frame, pivot_tol);
+        __syncthreads();
+#ifdef CHEQ_POTRF_INSTRUMENT
+        long long w1 = 0, wc = 0, w2 = 0;
+#endif
+        for (int k = 0; k < kTile - 1; ++k) {
+#ifdef CHEQ_POTRF_INSTRUMENT
+            const long long c0 = clock64();
+#endif
+            named_bar_sync(1, 64);
+#ifdef CHEQ_POTRF_INSTRUMENT
+            const long long c1 = clock64();
+#endif
+            cw_chain_step(k + 1, lane, colbuf[cur ^ 1], ubuf[cur ^ 1], keepbuf[cur ^ 1], dinv, sg, state, frame,
+                          pivot_tol);
+#ifdef CHEQ_POTRF_INSTRUMENT
+            const long long c2 = clock64();
+#endif
+            __syncthreads();
+#ifdef CHEQ_POTRF_INSTRUMENT
+            w1 += c1 - c0;
+            wc += c2 - c1;
+            w2 += clock64() - c2;
+#endif
+            cur ^= 1;
+        }
+#ifdef CHEQ_POTRF_INSTRUMENT
+        if (lane == 0) {
+            atomicAdd(&g_potrf_cycles[1], (unsigned long long)w1);   // wait for the raw column
+            atomicAdd(&g_potrf_cycles[2], (unsigned long long)wc);   // chain
+            atomicAdd(&g_potrf_cycles[3], (unsigned long long)w2);   // wait for the update warps
+            atomicAdd(&g_potrf_cycles[5], 1ull);
+        }
+#endif
+        __syncthreads();   // step 127 of the update warps
+        __syncthreads();   // epilogue barriers
+        __syncthreads();
+    } else {
+        // ---------------- update warps ----------------
+        double e[8][8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const int r = ty + 16 * a, c = tx + 16 * b;
+                e[a][b] = (r >= c) ? A[r + (long)c * lda] : 0.0;
+            }
+        const bool p_diag = ty >= tx;
+        int cur = 0;
+        if (tx == 0) {
+#pragma unroll
+            for (int a = 0; a < 8; ++a) colbuf[0][ty + 16 * a] = e[a][0];
+        }
+        if ((tx >> 1) == 0) named_bar_arrive(1, 64);
+        __syncthreads();
+        potrf_cw_block<0>(e, ty, tx, p_diag, cur, ubuf, colbuf, keepbuf, sg);
+        potrf_cw_block<1>(e, ty, tx, p_diag, cur, ubuf, colbuf, keepbuf, sg);
+        potrf_cw_block<2>(e, ty, tx, p_diag, cur, ubuf, colbuf, keepbuf, sg);
+        potrf_cw_block<3>(e, ty, tx, p_diag, cur, ubuf, colbuf, keepbuf, sg);
+        potrf_cw_block<4>(e, ty, tx, p_diag, cur, ubuf, colbuf, keepbuf, sg);
+        potrf_cw_block<5>(e, ty, tx, p_diag, cur, ubuf, colbuf, keepbuf, sg);
+        potrf_cw_block<6>(e, ty, tx, p_diag, cur, ubuf, colbuf, keepbuf, sg);
+        potrf_cw_block<7>(e, ty, tx, p_diag, cur, ubuf, colbuf, keepbuf, sg);
+
+        // L back to global; M = S X staged through shared memory (M[i][j] = s_i X[i][j], i > j, held as (j, i))
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+#pragma unroll
+            for (int a = 0; a < 8; ++a) {
+                const int r = ty + 16 * a, c = tx + 16 * b;
+                if (r >= c) A[r + (long)c * lda] = e[a][b];
+                double m = 0.0;
+                if (r < c) m = sg[c] * e[a][b];
+                else if (r == c) m = sg[r] * dinv[r];
+                Ms[r * kPotrfLd + c] = m;
+            }
+        __syncthreads();
+        for (int idx = t; idx < kTile * kTile; idx += kPotrfThreads) {
+            const int i = idx & (kTile - 1), j = idx >> 7;
+            Minv[idx] = Ms[j * kPotrfLd + i];
+        }
+        if (t < kTile && sgn_) sgn_[(long)frame * strideSgn + t] = sg[t];
+        if (t == 0 && neg_cnt_) {
+            int n = 0;
+            int* idx = neg_idx_ + (long)frame * strideNeg * kTile;
+            for (int i = 0; i < kTile; ++i)
+                if (sg[i] < 0.0) idx[n++] = i;
+            neg_cnt_[(long)frame * strideNeg] = n;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // Diagonal tile, DMMA-blocked variant (experimental, see launch_potrf_tile).  Same mathematics and outputs as potrf_tile_kernel, but the tile
 // is held in registers in DMMA accumulator layout (warp w owns tile rows 2w, 2w+1 of the 16 x 16 grid of 8 x 8
 // tiles; lane T holds rows T/4, columns 2 (T%4), +1 of each) and eliminated four columns at a time:
@@ -1536,6 +1768,23 @@ cudaError_t launch_potrf_tile(double* A, long lda, long strideA, double* Linv, l
     if (pp.n > 0) {   // only the default kernel knows how to push its outputs to peers
         potrf_tile_kernel<<<grid, kPotrfThreads, kPotrfSmem, stream>>>(A, lda, strideA, Linv, strideLinv, sgn, strideSgn,
                                                                        neg_cnt, neg_idx, strideNeg, state, pivot_tol, pp);
+        return cudaGetLastError();
+    }
+    // CHEQ_POTRF_CW=1: rank-1 updates with a dedicated chain warp.  Measured 8 % SLOWER than the plain kernel: the
+    // chain warp waits 5 cycles per step for its column and 13 for the update warps, but its own chain takes 883
+    // cycles instead of 390 -- its dependent DFMAs queue behind the update warps' independent DFMAs on the FP64
+    // pipe of the SM sub-partition they share (profiles/r1_potrf_variants.txt).
+    static const bool use_cw = [] { const char* e = getenv("CHEQ_POTRF_CW"); return e && e[0] == '1'; }();
+    if (use_scalar && use_rank1 && use_v1 && use_cw) {
+        static bool conf3 = false;
+        if (!conf3) {
+            cudaError_t e = cudaFuncSetAttribute(potrf_tile_cw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 kPotrfSmem);
+            if (e != cudaSuccess) return e;
+            conf3 = true;
+        }
+        potrf_tile_cw_kernel<<<grid, kCwThreads, kPotrfSmem, stream>>>(A, lda, strideA, Linv, strideLinv, sgn, strideSgn,
+                                                                       neg_cnt, neg_idx, strideNeg, state, pivot_tol);
         return cudaGetLastError();
     }
     if (use_scalar && use_rank1 && !use_v1) {
