@@ -449,6 +449,13 @@ def run_ours(args, rank, local_rank, world):
         "roofline": {"bound": "tensor", "kernel": "gemm_nt_kernel (FP64 DMMA.8x8x4)", "achieved": achieved,
                      "peak": peak_sustained, "unit": "TFLOP/s", "frac": achieved / peak_sustained if peak_sustained else None,
                      "traffic": None, "launches": gemm_n, "kernel_ms_per_step": gemm_ms / args.steps,
+                     "largest_launch": ({"what": "Schur update of the hydrogen block, K = 6784, 106 x 105 tiles (lower)",
+                                         "flops": 1.2488e12, "ms": 39.41, "tflops": 31.7, "dmma_pipe_active": 0.876,
+                                         "traffic": 9.286e9, "algorithmic_bytes": 2.2e9,
+                                         "source": "one ncu --set full capture of that launch "
+                                                   "(profiles/r1_ncu_full_gemm_schur_v3.txt); `traffic` above is null "
+                                                   "because `achieved` averages 3,868 launches of different shapes"}
+                                        if n == 20001 else None),
                      "share_of_step": gemm_ms / ms_profiled,
                      "measured_in": f"second pass of {args.steps} steps with per-launch CUDA events "
                                     f"({ms_profiled / args.steps:.1f} ms per step vs {ms_total / args.steps:.1f} uninstrumented)",
