@@ -601,6 +601,7 @@ potrf_tile_pipe_kernel(double* A_, long lda, long strideA, double* Minv_, long s
 // Step time: max(chain, update) instead of chain + update.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int kCwThreads = kPotrfThreads + 32;
+constexpr int kCwSoloThreads = 384;
 
 __device__ __forceinline__ void named_bar_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -701,12 +702,12 @@ __device__ __forceinline__ void potrf_cw_block(double (&e)[8][8], int ty, int tx
             for (int a = 0; a < 8; ++a)
                 if (POTRF_UPD(a, b, kb)) e[a][b] = fma(-su[a], uc, e[a][b]);
         }
-        __syncthreads();
+        named_bar_sync(2, kCwThreads);   // update warps + chain warp
         cur ^= 1;
     }
 }
 
-__global__ void __launch_bounds__(kCwThreads)
+__global__ void __launch_bounds__(kCwSoloThreads)
 potrf_tile_cw_kernel(double* A_, long lda, long strideA, double* Minv_, long strideM, double* sgn_, long strideSgn,
                      int* neg_cnt_, int* neg_idx_, long strideNeg, ScfState* state, double pivot_tol) {
     const int frame = blockIdx.z;
@@ -717,16 +718,30 @@ potrf_tile_cw_kernel(double* A_, long lda, long strideA, double* Minv_, long str
     __shared__ double sg[kTile];
     double* A = A_ + (long)frame * strideA;
     double* Minv = Minv_ + (long)frame * strideM;
-    const int t = threadIdx.x;
-    const int ty = t & 15, tx = t >> 4;            // tx == 16, 17: the chain warp
+    // Roles.  288 threads: warps 0-7 update, warp 8 runs the chain.  384 threads ("solo"): warps map to SM
+    // sub-partitions by warp % 4, so warps 0, 4, 8 share one; warp 0 runs the chain there ALONE (4 and 8 exit at
+    // once, as does 11), the eight update warps live on the other three sub-partitions and their FP64 pipes.
+    const int pw = threadIdx.x >> 5;
+    bool chain;
+    int lw;
+    if (blockDim.x == kCwThreads) {
+        chain = pw == 8;
+        lw = pw;
+    } else {
+        if (pw == 4 || pw == 8 || pw == 11) return;
+        chain = pw == 0;
+        lw = pw < 4 ? pw - 1 : (pw < 8 ? pw - 2 : pw - 3);
+    }
+    const int t = lw * 32 + (threadIdx.x & 31);   // logical thread of the 16 x 16 tile grid (update warps)
+    const int ty = t & 15, tx = t >> 4;
 
-    if (t >= kPotrfThreads) {
+    if (chain) {
         // ---------------- chain warp ----------------
-        const int lane = t & 31;
+        const int lane = threadIdx.x & 31;
         int cur = 0;
         named_bar_sync(1, 64);
         cw_chain_step(0, lane, colbuf[0], ubuf[0], keepbuf[0], dinv, sg, state, frame, pivot_tol);
-        __syncthreads();
+        named_bar_sync(2, kCwThreads);
 #ifdef CHEQ_POTRF_INSTRUMENT
         long long w1 = 0, wc = 0, w2 = 0;
 #endif
@@ -743,7 +758,7 @@ potrf_tile_cw_kernel(double* A_, long lda, long strideA, double* Minv_, long str
 #ifdef CHEQ_POTRF_INSTRUMENT
             const long long c2 = clock64();
 #endif
-            __syncthreads();
+            named_bar_sync(2, kCwThreads);
 #ifdef CHEQ_POTRF_INSTRUMENT
             w1 += c1 - c0;
             wc += c2 - c1;
@@ -759,9 +774,7 @@ potrf_tile_cw_kernel(double* A_, long lda, long strideA, double* Minv_, long str
             atomicAdd(&g_potrf_cycles[5], 1ull);
         }
 #endif
-        __syncthreads();   // step 127 of the update warps
-        __syncthreads();   // epilogue barriers
-        __syncthreads();
+        named_bar_sync(2, kCwThreads);   // step 127 of the update warps
     } else {
         // ---------------- update warps ----------------
         double e[8][8];
@@ -779,7 +792,7 @@ potrf_tile_cw_kernel(double* A_, long lda, long strideA, double* Minv_, long str
             for (int a = 0; a < 8; ++a) colbuf[0][ty + 16 * a] = e[a][0];
         }
         if ((tx >> 1) == 0) named_bar_arrive(1, 64);
-        __syncthreads();
+        named_bar_sync(2, kCwThreads);
         potrf_cw_block<0>(e, ty, tx, p_diag, cur, ubuf, colbuf, keepbuf, sg);
         potrf_cw_block<1>(e, ty, tx, p_diag, cur, ubuf, colbuf, keepbuf, sg);
         potrf_cw_block<2>(e, ty, tx, p_diag, cur, ubuf, colbuf, keepbuf, sg);
@@ -801,7 +814,7 @@ potrf_tile_cw_kernel(double* A_, long lda, long strideA, double* Minv_, long str
                 else if (r == c) m = sg[r] * dinv[r];
                 Ms[r * kPotrfLd + c] = m;
             }
-        __syncthreads();
+        named_bar_sync(3, kPotrfThreads);   // update warps only
         for (int idx = t; idx < kTile * kTile; idx += kPotrfThreads) {
             const int i = idx & (kTile - 1), j = idx >> 7;
             Minv[idx] = Ms[j * kPotrfLd + i];
@@ -814,7 +827,6 @@ potrf_tile_cw_kernel(double* A_, long lda, long strideA, double* Minv_, long str
                 if (sg[i] < 0.0) idx[n++] = i;
             neg_cnt_[(long)frame * strideNeg] = n;
         }
-        __syncthreads();
     }
 }
 
@@ -1774,7 +1786,8 @@ cudaError_t launch_potrf_tile(double* A, long lda, long strideA, double* Linv, l
     // chain warp waits 5 cycles per step for its column and 13 for the update warps, but its own chain takes 883
     // cycles instead of 390 -- its dependent DFMAs queue behind the update warps' independent DFMAs on the FP64
     // pipe of the SM sub-partition they share (profiles/r1_potrf_variants.txt).
-    static const bool use_cw = [] { const char* e = getenv("CHEQ_POTRF_CW"); return e && e[0] == '1'; }();
+    static const int cw_mode = [] { const char* e = getenv("CHEQ_POTRF_CW"); return e ? atoi(e) : 0; }();
+    static const bool use_cw = cw_mode == 1 || cw_mode == 2;
     if (use_scalar && use_rank1 && use_v1 && use_cw) {
         static bool conf3 = false;
         if (!conf3) {
@@ -1783,7 +1796,7 @@ cudaError_t launch_potrf_tile(double* A, long lda, long strideA, double* Linv, l
             if (e != cudaSuccess) return e;
             conf3 = true;
         }
-        potrf_tile_cw_kernel<<<grid, kCwThreads, kPotrfSmem, stream>>>(A, lda, strideA, Linv, strideLinv, sgn, strideSgn,
+        potrf_tile_cw_kernel<<<grid, cw_mode == 2 ? kCwSoloThreads : kCwThreads, kPotrfSmem, stream>>>(A, lda, strideA, Linv, strideLinv, sgn, strideSgn,
                                                                        neg_cnt, neg_idx, strideNeg, state, pivot_tol);
         return cudaGetLastError();
     }
