@@ -31,7 +31,9 @@ class Stats(C.Structure):
                 ("n_hydrogen", C.c_uint64), ("n_padded", C.c_uint64), ("iterations", C.c_uint32),
                 ("pair_types", C.c_uint32), ("flops_factor", C.c_double), ("bytes_assemble", C.c_double),
                 ("lu_fallback_frames", C.c_uint64), ("gemm_ms", C.c_double), ("gemm_flops", C.c_double),
-                ("gemm_launches", C.c_uint64), ("potrf_ms", C.c_double), ("backsolve_ms", C.c_double)]
+                ("gemm_launches", C.c_uint64), ("potrf_ms", C.c_double), ("backsolve_ms", C.c_double),
+                ("krylov_iterations", C.c_uint64), ("krylov_steps", C.c_uint64), ("krylov_ms", C.c_double),
+                ("krylov_bytes", C.c_double)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -47,6 +49,8 @@ SIGNATURES = {
     "cheq_get_stats": (_I32, [_P, C.POINTER(Stats)]),
     "cheq_ctx_stream": (_P, [_P]),
     "cheq_set_profiling": (_I32, [_P, _I32]),
+    "cheq_get_scf_trace": (_I32, [_P, C.c_uint32, _P, _P, _P, C.POINTER(C.c_uint32)]),
+    "cheq_set_krylov": (_I32, [_P, _I32, _I32, _D, _I32]),
     "cheq_dist_unique_id": (_I32, [_P]),
     "cheq_ctx_dist_init": (_I32, [_P, _I32, _I32, _P]),
     "cheq_ctx_dist_info": (_I32, [_P, C.POINTER(_I32), C.POINTER(_I32)]),

@@ -246,6 +246,18 @@ struct cheq_ctx {
     DeviceBuffer in_xyz, in_chi, in_hard, in_radius, in_nq, perm, type, x, y, z, diag, chi, hard, vext, A, S0,
         Linv, v, q, scratch, counters, state, active, blob, pc_xyz, pc_q, pc_type, out_q, misc0, misc1, misc2,
         lu_f, lu_piv, sgn, sgn_flags, xsol;
+    // stale-factor SCF iterations (kernels_krylov.cu): explicit R = L_hh^-T S of the frozen hydrogen factor, partial
+    // sums of the tiled matrix-vector products, the small vectors of GMRES, device / pinned-host scalars
+    DeviceBuffer kr_R, kr_part, kr_vec, kr_sc;
+    KrylovScalars* h_ksc = nullptr;   // pinned
+    int morton = 1;                   // CHEQ_MORTON=0: atoms of one element stay in input order (test knob: a
+                                      // different elimination order for the unpivoted factorisation)
+    int krylov_mode = 1;              // CHEQ_KRYLOV=0: refactor the hydrogen block in every SCF iteration
+    int krylov_min_nhp = 1024;        // CHEQ_KRYLOV_MIN_NH: smallest padded hydrogen block that uses the stale factor
+    double krylov_freeze_ev = 4.5;    // CHEQ_KRYLOV_FREEZE_EV: freeze once max |D_k - D_(k-1)| falls below this
+    int krylov_force_it = 5;          // ... or at this SCF iteration at the latest
+    struct TraceEntry { double delta; int mode; int steps; };   // mode 0: refactored, 1: stale factor + GMRES
+    std::vector<TraceEntry> trace;    // per SCF iteration of the last single-frame solve
     ScfState* h_state = nullptr;   // pinned
     int* h_active = nullptr;       // pinned
     size_t h_state_cap = 0;
@@ -356,7 +368,7 @@ int make_layout(cheq_ctx* ctx, long n, const double* radius, const uint8_t* nq, 
         else xs.push_back((int)i);
     }
     std::vector<uint32_t> code(n, 0);
-    if (xyz && n > 256) {
+    if (xyz && n > 256 && ctx->morton) {
         double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
         for (long i = 0; i < n; ++i)
             for (int d = 0; d < 3; ++d) {
@@ -1220,6 +1232,277 @@ int factor_blocked(Dense& D, int p_begin, int p_end) {
     return CHEQ_OK;
 }
 
+
+// ---- stale-factor SCF iterations: host side (kernels in kernels_krylov.cu) ---------------------------------------
+// Everything below works on the hydrogen block of ONE frame: n = nhp unknowns plus the border unknown mu.
+struct Krylov {
+    static constexpr int kMaxBasis = 48;        // GMRES restart length
+    static constexpr int kMaxSteps = 96;        // operator applications per SCF iteration before giving up
+    int nhp = 0, nt = 0, len = 0;               // len = nhp + 1 entries per vector
+    long vs = 0;                                // vector stride (doubles)
+    double *R = nullptr, *partN = nullptr, *partT = nullptr;
+    double *tc = nullptr, *t1 = nullptr, *ws = nullptr, *d_cur = nullptr, *d_prev = nullptr, *d_frozen = nullptr,
+           *sol = nullptr, *r = nullptr, *z = nullptr, *tmp1 = nullptr, *tmp2 = nullptr, *w = nullptr, *V = nullptr;
+    KrylovScalars* sc = nullptr;
+    const double* S0 = nullptr;
+    long ld0 = 0;
+    const double* sgn_h = nullptr;
+    bool ready = false;                         // buffers allocated, per-geometry scalars set
+    bool frozen = false;                        // R, ws, den describe the factor currently in the trapezoid
+    double bytes = 0.0;
+};
+
+int krylov_alloc(cheq_ctx* ctx, Krylov& K, int nhp) {
+    K.nhp = nhp;
+    K.nt = nhp / kTile;
+    K.len = nhp + 1;
+    K.vs = nhp + 8;
+    CU(ctx->kr_R.ensure((size_t)nhp * nhp * 8));
+    CU(ctx->kr_part.ensure((size_t)2 * K.nt * K.nt * kTile * 8));
+    const size_t nvec = 12 + Krylov::kMaxBasis + 1;
+    CU(ctx->kr_vec.ensure(nvec * K.vs * 8));
+    CU(ctx->kr_sc.ensure(sizeof(KrylovScalars)));
+    if (!ctx->h_ksc) CU(cudaMallocHost((void**)&ctx->h_ksc, sizeof(KrylovScalars)));
+    K.R = ctx->kr_R.as<double>();
+    K.partN = ctx->kr_part.as<double>();
+    K.partT = K.partN + (size_t)K.nt * K.nt * kTile;
+    double* v = ctx->kr_vec.as<double>();
+    double** slots[] = {&K.tc, &K.t1, &K.ws, &K.d_cur, &K.d_prev, &K.d_frozen, &K.sol, &K.r, &K.z, &K.tmp1, &K.tmp2, &K.w};
+    for (double** sl : slots) {
+        *sl = v;
+        v += K.vs;
+    }
+    K.V = v;
+    K.sc = (KrylovScalars*)ctx->kr_sc.p;
+    CU(cudaMemsetAsync(ctx->kr_vec.p, 0, nvec * K.vs * 8, ctx->stream));
+    CU(cudaMemsetAsync(ctx->kr_sc.p, 0, sizeof(KrylovScalars), ctx->stream));
+    return CHEQ_OK;
+}
+
+// out = S_s^-1 in = R S R^T in   (n entries; two passes over the upper triangle of R)
+int krylov_apply_sinv(cheq_ctx* ctx, Krylov& K, const double* in, double* out) {
+    cudaStream_t st = ctx->stream;
+    TileMatvecArgs a{};
+    a.M = K.R;
+    a.ld = K.nhp;
+    a.nt = K.nt;
+    a.upper = 1;
+    a.xT = in;
+    a.partN = K.partN;
+    a.partT = K.partT;
+    LAUNCH(launch_tile_matvec(a, false, true, st));
+    TileReduceArgs r{};
+    r.nt = K.nt;
+    r.upper = 1;
+    r.op = 0;
+    r.partT = K.partT;
+    r.out = K.tmp1;
+    LAUNCH(launch_tile_matvec_reduce(r, st));
+    a.xT = nullptr;
+    a.xN = K.tmp1;
+    a.scaleN = K.sgn_h;
+    LAUNCH(launch_tile_matvec(a, true, false, st));
+    r.partT = nullptr;
+    r.partN = K.partN;
+    r.out = out;
+    LAUNCH(launch_tile_matvec_reduce(r, st));
+    K.bytes += 8.0 * (double)K.nhp * (K.nhp + 1.0);
+    return CHEQ_OK;
+}
+
+// out = K_k v (op 1) or rhs - K_k v (op 2), K_k = [[S0 + D_k, t1], [t1^T, -g]]   (one pass over the lower triangle of S0)
+int krylov_apply_K(cheq_ctx* ctx, Krylov& K, const double* v, double* out, int op) {
+    cudaStream_t st = ctx->stream;
+    TileMatvecArgs a{};
+    a.M = K.S0;
+    a.ld = K.ld0;
+    a.nt = K.nt;
+    a.upper = 0;
+    a.sym = 1;
+    a.xN = v;
+    a.xT = v;
+    a.partN = K.partN;
+    a.partT = K.partT;
+    LAUNCH(launch_tile_matvec(a, true, true, st));
+    TileReduceArgs r{};
+    r.nt = K.nt;
+    r.upper = 0;
+    r.op = op;
+    r.partN = K.partN;
+    r.partT = K.partT;
+    r.v = v;
+    r.d = K.d_cur;
+    r.t1 = K.t1;
+    r.rhs = K.tc;
+    r.sc = K.sc;
+    r.out = out;
+    LAUNCH(launch_tile_matvec_reduce(r, st));
+    K.bytes += 4.0 * (double)K.nhp * (K.nhp + 1.0);
+    return CHEQ_OK;
+}
+
+// out = K_s^-1 in  (frozen factor + border elimination)
+int krylov_apply_precond(cheq_ctx* ctx, Krylov& K, const double* in, double* out) {
+    int rc = krylov_apply_sinv(ctx, K, in, K.tmp2);
+    if (rc) return rc;
+    LAUNCH(launch_precond_border(K.tmp2, in, K.t1, K.ws, K.sc, out, K.nhp, ctx->stream));
+    return CHEQ_OK;
+}
+
+// R = L_hh^-T S for the hydrogen factor currently in the trapezoid: right-hand triangular solve applied to the rows
+// of an identity, with the same kernel sequence as the rows below a panel in factor_panel (leaf: multiply by
+// M^T = (S L_jj^-1)^T; update: C -= A S B^T), restricted to the rows that can be non-zero.  n_h^3 / 3 flops.
+int krylov_build_R(Dense& D, Krylov& K, int h0, int j0, int n) {
+    cheq_ctx* ctx = D.ctx;
+    const long ldr = K.nhp;
+    if (n == kTile) {
+        GemmArgs g{};
+        g.A = K.R + (long)j0 * ldr;
+        g.lda = ldr;
+        g.B = D.Linv + (long)((h0 + j0) / kTile) * kTile * kTile;
+        g.ldb = kTile;
+        g.C = K.R + (long)j0 * ldr;
+        g.ldc = ldr;
+        g.K = kTile;
+        const int mt = (j0 + kTile) / kTile;
+        const double fl = 2.0 * mt * (double)kTile * kTile * kTile;
+        D.flops += fl;
+        return launch_gemm_timed(ctx, g, mt, 1, 1, fl);
+    }
+    const int n1 = ((n / kTile) / 2) * kTile;
+    int rc = krylov_build_R(D, K, h0, j0, n1);
+    if (rc) return rc;
+    {
+        GemmArgs g{};
+        g.A = K.R + (long)j0 * ldr;
+        g.lda = ldr;
+        g.B = D.A + (long)(h0 + j0 + n1) + (long)(h0 + j0) * D.ld;
+        g.ldb = D.ld;
+        g.C = K.R + (long)(j0 + n1) * ldr;
+        g.ldc = ldr;
+        g.K = n1;
+        g.subtract = 1;
+        g.neg_cnt = D.neg_cnt + (h0 + j0) / kTile;
+        g.neg_idx = D.neg_idx + (long)(h0 + j0);
+        g.strideNeg = D.strideNeg;
+        const int mt = (j0 + n1) / kTile, nt = (n - n1) / kTile;
+        const double fl = 2.0 * (double)(j0 + n1) * (double)(n - n1) * (double)n1;
+        D.flops += fl;
+        rc = launch_gemm_timed(ctx, g, mt, nt, 1, fl);
+        if (rc) return rc;
+    }
+    return krylov_build_R(D, K, h0, j0 + n1, n - n1);
+}
+
+// Freeze the factor that is in the trapezoid (it belongs to the diagonal shift `d_of_factor`).
+int krylov_freeze(cheq_ctx* ctx, Dense& D, Krylov& K, int nxp, const double* d_of_factor) {
+    cudaStream_t st = ctx->stream;
+    LAUNCH(launch_set_identity_tiles(K.R, K.nhp, K.nt, st));
+    int rc = krylov_build_R(D, K, nxp, 0, K.nhp);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(K.d_frozen, d_of_factor, (size_t)K.nhp * 8, cudaMemcpyDeviceToDevice, st));
+    rc = krylov_apply_sinv(ctx, K, K.t1, K.ws);
+    if (rc) return rc;
+    LAUNCH(launch_precond_den(K.t1, K.ws, K.sc, K.nhp, st));
+    K.frozen = true;
+    return CHEQ_OK;
+}
+
+// Solves K_k sol = [t_c; Q - h] with GMRES preconditioned by the frozen K_s^-1, restarted from the true residual
+// until the preconditioned residual (an estimate of the error itself) is below tol * |sol|.  `sol` holds the
+// previous iteration's solution on entry.  Returns the operator applications in *steps; *ok = false if it did not
+// get there (the caller then refactors).
+int krylov_solve(cheq_ctx* ctx, Krylov& K, double tol, int* steps, bool* ok) {
+    cudaStream_t st = ctx->stream;
+    KrylovScalars* hs = ctx->h_ksc;
+    constexpr int m = Krylov::kMaxBasis;
+    static thread_local double H[(m + 1) * m];
+    double cs[m], sn[m], gv[m + 1], y[m];
+    *steps = 0;
+    *ok = false;
+    static const bool debug = [] { const char* e = getenv("CHEQ_KRYLOV_DEBUG"); return e && e[0] == '1'; }();
+    double scale = 0.0, beta_prev = 0.0;
+    for (int cycle = 0; cycle < 8; ++cycle) {
+        // true residual, preconditioned: z = K_s^-1 (b - K_k sol)
+        int rc = krylov_apply_K(ctx, K, K.sol, K.r, 2);
+        if (rc) return rc;
+        rc = krylov_apply_precond(ctx, K, K.r, K.z);
+        if (rc) return rc;
+        *steps += 1;
+        LAUNCH(launch_multi_dot(nullptr, 0, K.z, K.len, K.sc->dots, 0, true, st));
+        if (cycle == 0) LAUNCH(launch_multi_dot(nullptr, 0, K.sol, K.len, K.sc->dots + 1, 0, true, st));
+        CU(cudaMemcpyAsync(hs->dots, K.sc->dots, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        const double beta = std::sqrt(hs->dots[0]);
+        if (cycle == 0) scale = std::max(std::sqrt(hs->dots[1]), 1e-300);
+        if (debug) fprintf(stderr, "[krylov] cycle %d steps %d  |P r| = %.3e  |sol| = %.3e\n", cycle, *steps, beta, scale);
+        if (!std::isfinite(beta)) return CHEQ_OK;                        // not ok
+        if (beta <= tol * scale) {
+            *ok = true;
+            return CHEQ_OK;
+        }
+        if (cycle > 0 && beta > 0.25 * beta_prev) {
+            // rounding floor of this system (or a stalled restart): accept only if it is far below the parity budget
+            *ok = beta <= 1e3 * tol * scale;
+            return CHEQ_OK;
+        }
+        if (*steps >= Krylov::kMaxSteps) return CHEQ_OK;
+        beta_prev = beta;
+        LAUNCH(launch_scale_by_rnorm(K.z, K.V, K.len, K.sc->dots, st));
+        gv[0] = beta;
+        int k = 0;
+        for (int j = 0; j < m; ++j) {
+            const double* vj = K.V + (long)j * K.vs;
+            rc = krylov_apply_K(ctx, K, vj, K.r, 1);
+            if (rc) return rc;
+            rc = krylov_apply_precond(ctx, K, K.r, K.w);
+            if (rc) return rc;
+            *steps += 1;
+            // classical Gram-Schmidt, twice
+            LAUNCH(launch_multi_dot(K.V, K.vs, K.w, K.len, K.sc->dots, j + 1, false, st));
+            LAUNCH(launch_gs_update(K.V, K.vs, K.w, K.len, K.sc->dots, K.sc->hsum, j + 1, true, st));
+            LAUNCH(launch_multi_dot(K.V, K.vs, K.w, K.len, K.sc->dots, j + 1, false, st));
+            LAUNCH(launch_gs_update(K.V, K.vs, K.w, K.len, K.sc->dots, K.sc->hsum, j + 1, false, st));
+            LAUNCH(launch_multi_dot(nullptr, 0, K.w, K.len, K.sc->dots + (m + 8), 0, true, st));
+            CU(cudaMemcpyAsync(hs->hsum, K.sc->hsum, (j + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(hs->dots + (m + 8), K.sc->dots + (m + 8), sizeof(double), cudaMemcpyDeviceToHost, st));
+            if (j + 1 < m)
+                LAUNCH(launch_scale_by_rnorm(K.w, K.V + (long)(j + 1) * K.vs, K.len, K.sc->dots + (m + 8), st));
+            CU(cudaStreamSynchronize(st));
+            for (int i = 0; i <= j; ++i) H[i * m + j] = hs->hsum[i];
+            double hn = std::sqrt(std::max(0.0, hs->dots[m + 8]));
+            for (int i = 0; i < j; ++i) {
+                const double a = cs[i] * H[i * m + j] + sn[i] * H[(i + 1) * m + j];
+                H[(i + 1) * m + j] = -sn[i] * H[i * m + j] + cs[i] * H[(i + 1) * m + j];
+                H[i * m + j] = a;
+            }
+            const double rr = std::hypot(H[j * m + j], hn);
+            if (!(rr > 0.0) || !std::isfinite(rr)) {
+                k = j;
+                break;
+            }
+            cs[j] = H[j * m + j] / rr;
+            sn[j] = hn / rr;
+            H[j * m + j] = rr;
+            gv[j + 1] = -sn[j] * gv[j];
+            gv[j] = cs[j] * gv[j];
+            k = j + 1;
+            if (debug) fprintf(stderr, "[krylov]   step %d  estimate %.3e\n", j, std::fabs(gv[j + 1]));
+            if (std::fabs(gv[j + 1]) <= 0.3 * tol * scale || *steps >= Krylov::kMaxSteps) break;
+        }
+        if (k == 0) return CHEQ_OK;
+        for (int i = k - 1; i >= 0; --i) {
+            double sacc = gv[i];
+            for (int c = i + 1; c < k; ++c) sacc -= H[i * m + c] * y[c];
+            y[i] = sacc / H[i * m + i];
+        }
+        for (int i = 0; i < k; ++i) hs->y[i] = y[i];
+        CU(cudaMemcpyAsync(K.sc->y, hs->y, k * sizeof(double), cudaMemcpyHostToDevice, st));
+        LAUNCH(launch_combine(K.V, K.vs, K.sol, K.len, K.sc->y, k, st));
+    }
+    return CHEQ_OK;
+}
+
 int ensure_host_state(cheq_ctx* ctx, size_t batch) {
     if (batch <= ctx->h_state_cap) return CHEQ_OK;
     if (ctx->h_state) cudaFreeHost(ctx->h_state);
@@ -1243,6 +1526,10 @@ struct SolveIO {
     uint32_t* iterations_out = nullptr;
     double* delta_out = nullptr;
     int32_t* status_out = nullptr;   // batch only
+    // true only for cheq_solve / cheq_solve_device: on a context that joined a group these calls are COLLECTIVE
+    // (every rank calls them with identical inputs).  cheq_solve_batch and the component entry points are always
+    // local, whatever the chunk size: a one-frame chunk of a batch must never enter the group's factorisation.
+    bool collective = false;
 };
 
 int validate_options(cheq_ctx* ctx, const cheq_options* o) {
@@ -1276,8 +1563,26 @@ struct Prepared {
 bool use_blocked(const cheq_ctx* ctx, int batch, long NP) {
     (void)NP;
     if (batch != 1) return false;
+    // ctx->world is 1 for the duration of a non-collective call on a joined context (LocalCallGuard)
     return ctx->world > 1 || ctx->factor_mode == 1;
 }
+
+// A context that joined a group runs its non-collective calls (batches, component entry points) as a single GPU:
+// rank / world are masked for the duration of the call (the caller holds ctx->mu).
+struct LocalCallGuard {
+    cheq_ctx* ctx;
+    int rank, world;
+    LocalCallGuard(cheq_ctx* c, bool collective) : ctx(c), rank(c->rank), world(c->world) {
+        if (!collective) {
+            ctx->rank = 0;
+            ctx->world = 1;
+        }
+    }
+    ~LocalCallGuard() {
+        ctx->rank = rank;
+        ctx->world = world;
+    }
+};
 
 int prepare_and_assemble(cheq_ctx* ctx, const SolveIO& io, long frame0, int batch, bool hydrogen_scf,
                          Prepared& P, bool topology_ready, bool all_columns = false) {
@@ -1579,20 +1884,104 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
 
     const uint8_t* type_h = ctx->type.as<uint8_t>() + L.nxp;
     const double* hard_h = ctx->hard.as<double>() + L.nxp;
+
+    // Stale-factor iterations (kernels_krylov.cu): one frame, one GPU, a hydrogen block that is worth it, and room
+    // for R (nhp^2 doubles).  Otherwise every iteration refactors the hydrogen block.
+    Krylov K;
+    bool kry = batch == 1 && !dist && ctx->krylov_mode && L.nhp >= ctx->krylov_min_nhp;
+    if (kry) {
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        const size_t need = (size_t)L.nhp * L.nhp * 8 + ((size_t)64 << 20);
+        if (need > free_b + ctx->kr_R.cap) kry = false;
+    }
+    if (kry) {
+        rc = krylov_alloc(ctx, K, L.nhp);
+        if (rc) return rc;
+        K.S0 = ctx->S0.as<double>();
+        K.ld0 = ld0;
+        K.sgn_h = D.sgn + L.nxp;
+        LAUNCH(launch_krylov_setup(D.A, D.ld, L.NP, L.nxp, D.sgn, K.S0, ld0, L.nhp, io.total_charge, K.sc, K.tc, K.t1, st));
+    }
+    cudaEvent_t evk0 = ctx->ev[5], evk1 = ctx->ev[6];
+    float krylov_ms = 0.0f;
+    bool have_factor = false;        // the trapezoid's hydrogen block holds the factor for the shift in K.d_prev
     uint32_t it = 0;
     double flops_iter_total = 0.0;
     for (it = 1; it <= o.max_iterations; ++it) {
-        if (it > 1)
-            LAUNCH(launch_copy_lower_tiles(ctx->S0.as<double>(), ld0, stride0, Ahh, L.ld, D.strideA, mt_h, nt_h,
-                                           D.state, batch, st, mask_h));
-        LAUNCH(launch_set_h_diagonal(Ahh, L.ld, D.strideA, ctx->S0.as<double>(), ld0, stride0, hard_h,
-                                     q + L.nxp, L.NP, type_h, L.nhp, D.state, batch, st, mask_h));
-        D.flops = 0.0;
-        rc = blocked ? factor_blocked(D, pp.x_panels, (int)pp.begin.size()) : factor_panel(D, L.nxp, L.nhp);
-        if (rc) return rc;
-        LAUNCH(launch_mu(D.A, D.ld, D.strideA, L.NP, io.total_charge, v, L.NP, D.sgn, D.strideSgn, D.state, batch, st));
-        rc = backsolve(D, L.NP, v, xs, L.NP);
-        if (rc) return rc;
+        bool use_krylov = false;
+        int gm_steps = 0;
+        if (kry) {
+            // this iteration's diagonal shift and how far it is from the factor we hold
+            CU(cudaMemsetAsync(&K.sc->dmax_bits, 0, sizeof(unsigned long long), st));
+            LAUNCH(launch_h_shift(hard_h, q + L.nxp, type_h, L.nhp, K.d_cur, K.frozen ? K.d_frozen : K.d_prev, K.sc, st));
+            if (K.frozen) {
+                use_krylov = true;
+            } else if (have_factor && it >= 2) {
+                CU(cudaMemcpyAsync(&ctx->h_ksc->dmax_bits, &K.sc->dmax_bits, sizeof(unsigned long long),
+                                   cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                double dmax;
+                std::memcpy(&dmax, &ctx->h_ksc->dmax_bits, 8);
+                if (dmax <= ctx->krylov_freeze_ev || (int)it >= ctx->krylov_force_it) {
+                    // the factor of the previous iteration becomes the preconditioner of all that follow
+                    CU(cudaEventRecord(evk0, st));
+                    D.flops = 0.0;
+                    rc = krylov_freeze(ctx, D, K, L.nxp, K.d_prev);
+                    if (rc) return rc;
+                    flops_iter_total += D.flops;
+                    CU(cudaEventRecord(evk1, st));
+                    use_krylov = true;
+                    CU(cudaStreamSynchronize(st));
+                    float ms = 0;
+                    cudaEventElapsedTime(&ms, evk0, evk1);
+                    krylov_ms += ms;
+                }
+            }
+        }
+        if (use_krylov) {
+            CU(cudaEventRecord(evk0, st));
+            bool ok = false;
+            rc = krylov_solve(ctx, K, 1e-13, &gm_steps, &ok);
+            if (rc) return rc;
+            if (ok) {
+                LAUNCH(launch_krylov_finish(D.A, D.ld, L.NP, L.nxp, K.sol, L.nhp, v, xs, D.state, st));
+                if (int rcp = prof_begin(ctx, 2)) return rcp;
+                CU(ctx->chain.ensure((size_t)(L.NP / kTile + 1) * sizeof(unsigned)));
+                LAUNCH(launch_backsolve_chain(D.A, D.ld, D.strideA, D.Linv, D.strideLinv, D.sgn, D.strideSgn, L.NP, v,
+                                              xs, L.NP, ctx->chain.as<unsigned>(), D.state, 1, st, L.nxp / kTile));
+                if (int rcp = prof_end(ctx)) return rcp;
+            } else {
+                // GMRES did not reach the target with this factor: refactor at the current shift instead
+                use_krylov = false;
+                K.frozen = false;
+            }
+            CU(cudaEventRecord(evk1, st));
+            CU(cudaStreamSynchronize(st));
+            float ms = 0;
+            cudaEventElapsedTime(&ms, evk0, evk1);
+            krylov_ms += ms;
+        }
+        if (!use_krylov) {
+            if (it > 1)
+                LAUNCH(launch_copy_lower_tiles(ctx->S0.as<double>(), ld0, stride0, Ahh, L.ld, D.strideA, mt_h, nt_h,
+                                               D.state, batch, st, mask_h));
+            LAUNCH(launch_set_h_diagonal(Ahh, L.ld, D.strideA, ctx->S0.as<double>(), ld0, stride0, hard_h,
+                                         q + L.nxp, L.NP, type_h, L.nhp, D.state, batch, st, mask_h));
+            D.flops = 0.0;
+            rc = blocked ? factor_blocked(D, pp.x_panels, (int)pp.begin.size()) : factor_panel(D, L.nxp, L.nhp);
+            if (rc) return rc;
+            LAUNCH(launch_mu(D.A, D.ld, D.strideA, L.NP, io.total_charge, v, L.NP, D.sgn, D.strideSgn, D.state, batch, st));
+            rc = backsolve(D, L.NP, v, xs, L.NP);
+            if (rc) return rc;
+            flops_iter_total += D.flops * (double)batch;   // upper bound for batches (finished frames skip)
+            if (kry) {
+                // remember which shift this factor belongs to, and its solution as the next initial guess
+                std::swap(K.d_cur, K.d_prev);
+                LAUNCH(launch_krylov_capture(xs, L.nxp, L.nhp, D.state, K.sol, st));
+                have_factor = true;
+            }
+        }
         LAUNCH(launch_scf_mix(xs, q, L.NP, ctx->type.as<uint8_t>(), L.NP, D.state, batch, st));
         CU(cudaMemsetAsync(ctx->active.p, 0, sizeof(int), st));
         LAUNCH(launch_scf_decide(D.state, o.tolerance, o.damping_kind, batch, ctx->active.as<int>(), st));
@@ -1611,14 +2000,18 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
                                 ctx->comm, ps));
             NC(g_nccl.GroupEnd());
             CU(cudaMemcpyAsync(ctx->h_active, ctx->active.p, sizeof(int), cudaMemcpyDeviceToHost, ps));
+            if (batch == 1) CU(cudaMemcpyAsync(ctx->h_state, ctx->state.p, sizeof(ScfState), cudaMemcpyDeviceToHost, ps));
             CU(cudaStreamSynchronize(ps));
         } else {
             CU(cudaMemcpyAsync(ctx->h_active, ctx->active.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            if (batch == 1) CU(cudaMemcpyAsync(ctx->h_state, ctx->state.p, sizeof(ScfState), cudaMemcpyDeviceToHost, st));
         }
         CU(cudaStreamSynchronize(st));
-        flops_iter_total += D.flops * (double)batch;   // upper bound for batches (finished frames skip)
+        if (batch == 1) ctx->trace.push_back({ctx->h_state[0].delta, use_krylov ? 1 : 0, gm_steps});
         if (*ctx->h_active == 0) break;
     }
+    ctx->stats.krylov_ms += krylov_ms;
+    ctx->stats.krylov_bytes += K.bytes;
     CU(cudaMemcpyAsync(ctx->h_state, ctx->state.p, sizeof(ScfState) * batch, cudaMemcpyDeviceToHost, st));
     CU(cudaEventRecord(ctx->ev[4], st));
     CU(cudaStreamSynchronize(st));
@@ -1671,7 +2064,10 @@ int lu_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
 }
 
 // Scatter + download the charges of `batch` frames starting at global frame gf0, and fill the scalar outputs.
-int emit_results(cheq_ctx* ctx, const SolveIO& io, const Prepared& P, long gf0, int batch, int* worst) {
+// `redo` (nullable): frames of the chunk that the pivoted-LU pass re-solves afterwards; their provisional status
+// does not count towards `worst`.
+int emit_results(cheq_ctx* ctx, const SolveIO& io, const Prepared& P, long gf0, int batch, int* worst,
+                 const std::vector<int>* redo = nullptr) {
     cudaStream_t st = ctx->stream;
     const long n = io.n;
     double* d_out;
@@ -1698,7 +2094,8 @@ int emit_results(cheq_ctx* ctx, const SolveIO& io, const Prepared& P, long gf0, 
         if (io.iterations_out) io.iterations_out[gf] = P.L.scf ? (uint32_t)s.iteration : 1u;
         if (io.delta_out) io.delta_out[gf] = s.delta;
         if (io.status_out) io.status_out[gf] = fs;
-        if (fs != CHEQ_OK && *worst == CHEQ_OK) {
+        const bool redone = redo && std::find(redo->begin(), redo->end(), f) != redo->end();
+        if (fs != CHEQ_OK && *worst == CHEQ_OK && !redone) {
             *worst = fs;
             if (fs == CHEQ_ERR_LINALG) {
                 ctx->err = "Linear system solver panicked. Matrix might be singular.";
@@ -1716,19 +2113,32 @@ int emit_results(cheq_ctx* ctx, const SolveIO& io, const Prepared& P, long gf0, 
 
 int solve_impl(cheq_ctx* ctx, const SolveIO& io) {
     std::lock_guard<std::mutex> lock(ctx->mu);
+    LocalCallGuard local_guard(ctx, io.collective && io.frames == 1);
     auto t_total = Clock::now();
     ctx->err.clear();
     ctx->stats = cheq_stats{};
     ctx->launches = 0;
     ctx->prof_used = 0;
     ctx->prof_flops = 0.0;
+    ctx->trace.clear();
     if (io.n == 0) return fail(ctx, CHEQ_ERR_NO_ATOMS, "Input validation failed: at least one atom is required for a calculation");
     int rc = validate_options(ctx, io.opt);
     if (rc) return rc;
     if (!io.xyz || !io.chi || !io.hard || !io.radius || !io.nq || !io.charges_out)
         return fail(ctx, CHEQ_ERR_INVALID_ARGUMENT, "NULL array argument");
-    if (io.n > 2000000) return fail(ctx, CHEQ_ERR_INVALID_ARGUMENT, "too many atoms for a dense solve");
     CU(cudaSetDevice(ctx->device));
+    {
+        // the dense direct path needs the lower trapezoid (+ the hydrogen snapshot): say so before allocating
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        const double np = (double)io.n + 2.0 * kTile;
+        const double need = 8.0 * np * (np + kRhsRows);
+        if (need > (double)total_b)
+            return fail(ctx, CHEQ_ERR_OUT_OF_MEMORY,
+                        "dense direct solve of " + std::to_string(io.n) + " atoms needs at least " +
+                            std::to_string((size_t)(need / 1073741824.0)) + " GiB for the matrix; the device has " +
+                            std::to_string(total_b >> 30) + " GiB (use the matrix-free path: cheq_solve_iterative)");
+    }
     const long n = io.n;
 
     // frames per chunk from the memory budget (single solve: 1)
@@ -1773,8 +2183,7 @@ int solve_impl(cheq_ctx* ctx, const SolveIO& io) {
             ctx->stats.lu_fallback_frames += 1;
             not_spd.clear();
         }
-        int chunk_worst = CHEQ_OK;
-        rc = emit_results(ctx, io, P, f0, batch, not_spd.empty() ? &worst : &chunk_worst);
+        rc = emit_results(ctx, io, P, f0, batch, &worst, &not_spd);
         if (rc) return rc;
         // batched frames that were not positive definite: one LU solve each, results overwrite the frame's slots
         for (int f : not_spd) {
@@ -1786,12 +2195,8 @@ int solve_impl(cheq_ctx* ctx, const SolveIO& io) {
             rc = emit_results(ctx, io, P, f0 + f, 1, &worst);
             if (rc) return rc;
         }
-        if (!not_spd.empty()) {
-            // statuses of the other frames of this chunk were written by the first emit; fold them into `worst`
-            if (io.status_out)
-                for (int f = 0; f < batch; ++f)
-                    if (io.status_out[f0 + f] != CHEQ_OK && worst == CHEQ_OK) worst = io.status_out[f0 + f];
-        }
+        // (the statuses of the chunk's other frames were folded into `worst` by emit_results: it skips exactly
+        //  the frames listed in `redo`)
     }
     ctx->stats.kernel_launches = ctx->launches;
     if (ctx->profile) {
@@ -1819,6 +2224,13 @@ int solve_impl(cheq_ctx* ctx, const SolveIO& io) {
         ctx->stats.backsolve_ms = ms_sum[2];
     }
     ctx->stats.ms_total = ms_since(t_total);
+    ctx->stats.krylov_iterations = 0;
+    ctx->stats.krylov_steps = 0;
+    for (const auto& te : ctx->trace)
+        if (te.mode == 1) {
+            ctx->stats.krylov_iterations += 1;
+            ctx->stats.krylov_steps += (uint64_t)te.steps;
+        }
     if (io.frames > 1 && io.status_out) return CHEQ_OK;
     return worst;
 }
@@ -1868,6 +2280,16 @@ int32_t cheq_ctx_create(int32_t device, cheq_ctx** out) {
             delete ctx;
             return CHEQ_ERR_CUDA;
         }
+    if (configure_dense_kernels() != cudaSuccess) {
+        cudaGetLastError();
+        cheq_ctx_destroy(ctx);
+        return CHEQ_ERR_CUDA;
+    }
+    if (const char* env = getenv("CHEQ_MORTON")) ctx->morton = atoi(env) != 0;
+    if (const char* env = getenv("CHEQ_KRYLOV")) ctx->krylov_mode = atoi(env) != 0;
+    if (const char* env = getenv("CHEQ_KRYLOV_MIN_NH")) ctx->krylov_min_nhp = std::max(128, atoi(env));
+    if (const char* env = getenv("CHEQ_KRYLOV_FREEZE_EV")) ctx->krylov_freeze_ev = atof(env);
+    if (const char* env = getenv("CHEQ_KRYLOV_FORCE_IT")) ctx->krylov_force_it = std::max(2, atoi(env));
     if (const char* env = getenv("CHEQ_PANEL_FLAT")) ctx->panel_flat = atoi(env) != 0;
     if (const char* env = getenv("CHEQ_FACTOR_MODE")) ctx->factor_mode = std::max(0, std::min(2, atoi(env)));
     if (const char* env = getenv("CHEQ_TILES_PER_PANEL")) ctx->tiles_per_panel = std::max(1, std::min(64, atoi(env)));
@@ -1909,6 +2331,11 @@ void cheq_ctx_destroy(cheq_ctx* ctx) {
                             &ctx->state, &ctx->active, &ctx->blob, &ctx->pc_xyz, &ctx->pc_q, &ctx->pc_type,
                             &ctx->out_q, &ctx->misc0, &ctx->misc1, &ctx->misc2, &ctx->lu_f, &ctx->lu_piv, &ctx->sgn, &ctx->sgn_flags, &ctx->xsol};
     for (DeviceBuffer* b : bufs) b->release();
+    ctx->kr_R.release();
+    ctx->kr_part.release();
+    ctx->kr_vec.release();
+    ctx->kr_sc.release();
+    if (ctx->h_ksc) cudaFreeHost(ctx->h_ksc);
     if (ctx->h_state) cudaFreeHost(ctx->h_state);
     if (ctx->h_active) cudaFreeHost(ctx->h_active);
     for (auto& e : ctx->ev)
@@ -1946,6 +2373,29 @@ int32_t cheq_set_profiling(cheq_ctx* ctx, int32_t enabled) {
     if (!ctx) return CHEQ_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(ctx->mu);
     ctx->profile = enabled != 0;
+    return CHEQ_OK;
+}
+
+int32_t cheq_get_scf_trace(const cheq_ctx* ctx, uint32_t capacity, double* delta_out, int32_t* mode_out,
+                           int32_t* steps_out, uint32_t* count_out) {
+    if (!ctx || !count_out) return CHEQ_ERR_INVALID_ARGUMENT;
+    const uint32_t n = (uint32_t)ctx->trace.size();
+    *count_out = n;
+    for (uint32_t i = 0; i < n && i < capacity; ++i) {
+        if (delta_out) delta_out[i] = ctx->trace[i].delta;
+        if (mode_out) mode_out[i] = ctx->trace[i].mode;
+        if (steps_out) steps_out[i] = ctx->trace[i].steps;
+    }
+    return CHEQ_OK;
+}
+
+int32_t cheq_set_krylov(cheq_ctx* ctx, int32_t enabled, int32_t min_hydrogen, double freeze_ev, int32_t force_iteration) {
+    if (!ctx) return CHEQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (enabled >= 0) ctx->krylov_mode = enabled != 0;
+    if (min_hydrogen > 0) ctx->krylov_min_nhp = std::max(128, (int)min_hydrogen);
+    if (freeze_ev > 0.0) ctx->krylov_freeze_ev = freeze_ev;
+    if (force_iteration > 0) ctx->krylov_force_it = std::max(2, (int)force_iteration);
     return CHEQ_OK;
 }
 
@@ -2027,6 +2477,7 @@ int32_t cheq_solve(cheq_ctx* ctx, uint64_t n_atoms, const double* xyz, const dou
     io.potential_out = potential_out;
     io.iterations_out = iterations_out;
     io.delta_out = delta_out;
+    io.collective = true;
     return solve_impl(ctx, io);
 }
 
@@ -2051,6 +2502,7 @@ int32_t cheq_solve_device(cheq_ctx* ctx, uint64_t n_atoms, const double* d_xyz, 
     io.potential_out = potential_out;
     io.iterations_out = iterations_out;
     io.delta_out = delta_out;
+    io.collective = true;
     return solve_impl(ctx, io);
 }
 
@@ -2127,6 +2579,7 @@ int32_t cheq_assemble_matrix(cheq_ctx* ctx, uint64_t n_atoms, const double* xyz,
     ctx->stats = cheq_stats{};
     ctx->launches = 0;
     if (n_atoms == 0) return fail(ctx, CHEQ_ERR_NO_ATOMS, "no atoms");
+    LocalCallGuard local_guard(ctx, false);
     CU(cudaSetDevice(ctx->device));
     cheq_options o;
     cheq_options_default(&o);
@@ -2166,6 +2619,7 @@ int32_t cheq_external_potential(cheq_ctx* ctx, uint64_t n_atoms, const double* x
     ctx->launches = 0;
     if (n_atoms == 0) return fail(ctx, CHEQ_ERR_NO_ATOMS, "no atoms");
     if (!external) return fail(ctx, CHEQ_ERR_INVALID_ARGUMENT, "external is NULL");
+    LocalCallGuard local_guard(ctx, false);
     CU(cudaSetDevice(ctx->device));
     cheq_options o;
     cheq_options_default(&o);

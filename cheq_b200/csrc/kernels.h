@@ -131,10 +131,13 @@ cudaError_t launch_backsolve_step(const double* A, long lda, long strideA, const
 int backsolve_max_ctas();
 // the whole backward substitution as one kernel (chain of CTAs linked by flags); work: batch * (NP / 128 + 1)
 // unsigned (tickets + flags, cleared by the launcher); v is not modified
+// nb_solve >= 0: only blocks [0, nb_solve) are solved; x of the blocks from nb_solve on is already in place
 cudaError_t launch_backsolve_chain(const double* A, long lda, long strideA, const double* Linv, long strideLinv,
                                    const double* sgn, long strideSgn, int NP, const double* v, double* x,
                                    long v_stride, unsigned* work, const ScfState* state, int batch,
-                                   cudaStream_t stream);
+                                   cudaStream_t stream, int nb_solve = -1);
+// per-device opt-in to large dynamic shared memory for every dense kernel (call after cudaSetDevice)
+cudaError_t configure_dense_kernels();
 // debug: accumulated cycle counters of the blocked diagonal-tile kernel {load, A, B, C, store, launches, -, -}
 cudaError_t potrf_debug_cycles(unsigned long long* out, int reset);
 // delta = max |x - q| over real atoms; q <- (1 - d) q + d x
@@ -144,6 +147,68 @@ cudaError_t launch_scf_mix(const double* x, double* q, long stride, const uint8_
 cudaError_t launch_scf_decide(ScfState* state, double tolerance, int damping_kind, int batch, int* active_count,
                               cudaStream_t stream);
 cudaError_t launch_scf_init(ScfState* state, double damping, int batch, cudaStream_t stream);
+
+// ---- stale-factor SCF iterations (kernels_krylov.cu) ------------------------------------------------------------
+// Device-resident scalars of the reduced bordered hydrogen system (see kernels_krylov.cu)
+struct KrylovScalars {
+    double g, h;                    // 1_x^T A_xx^-1 1_x,  1_x^T A_xx^-1 c_x
+    double den;                     // t1 . (S_s^-1 t1) + g of the frozen factor
+    unsigned long long dmax_bits;   // running max |d_new - d_ref| (positive doubles compare as integers)
+    double dots[72];                // Gram-Schmidt coefficients of the current step, then w . w
+    double hsum[72];                // accumulated coefficients of both Gram-Schmidt passes
+    double y[72];                   // least-squares solution uploaded by the host
+};
+
+struct TileMatvecArgs {
+    const double* M;   // nt x nt tiles of 128, column-major
+    long ld;
+    int nt;
+    int upper;         // 0: tiles i >= j hold the data (lower), 1: tiles i <= j (upper)
+    int sym;           // symmetric matrix stored as its lower triangle (N and T products in one pass)
+    const double* xN;  // N product:  pN[tile rows] = T x[tile columns]
+    const double* xT;  // T product:  pT[tile columns] = T^T x[tile rows]
+    const double* scaleN;   // nullable: x is scaled entry-wise (pivot signs)
+    const double* scaleT;
+    double* partN;     // [nt * nt][128] partial results per tile
+    double* partT;
+    const uint8_t* col_mask;   // nullable: tile columns owned by this rank
+};
+
+struct TileReduceArgs {
+    int nt, upper, op;
+    const double* partN;   // nullable
+    const double* partT;   // nullable
+    const uint8_t* col_mask;
+    const double* v;       // op 1, 2: the vector that was multiplied (n + 1 entries)
+    const double* d;       // op 1, 2: diagonal shift D_k
+    const double* t1;      // op 1, 2
+    const double* rhs;     // op 2
+    const KrylovScalars* sc;
+    double* out;
+};
+
+cudaError_t launch_tile_matvec(const TileMatvecArgs& a, bool do_n, bool do_t, cudaStream_t stream);
+cudaError_t launch_tile_matvec_reduce(const TileReduceArgs& a, cudaStream_t stream);
+cudaError_t launch_multi_dot(const double* V, long stride, const double* w, int len, double* out, int m,
+                             bool with_norm, cudaStream_t stream);
+cudaError_t launch_gs_update(const double* V, long stride, double* w, int len, const double* h, double* hsum, int m,
+                             bool first, cudaStream_t stream);
+cudaError_t launch_scale_by_rnorm(const double* src, double* dst, int len, const double* norm2, cudaStream_t stream);
+cudaError_t launch_combine(const double* V, long stride, double* x, int len, const double* y, int m,
+                           cudaStream_t stream);
+cudaError_t launch_precond_border(const double* u0, const double* rin, const double* t1, const double* ws,
+                                  const KrylovScalars* sc, double* out, int n, cudaStream_t stream);
+cudaError_t launch_precond_den(const double* t1, const double* ws, KrylovScalars* sc, int n, cudaStream_t stream);
+cudaError_t launch_krylov_setup(const double* A, long lda, int NP, int nxp, const double* sgn, const double* S0,
+                                long ld0, int nhp, double total_charge, KrylovScalars* sc, double* tc, double* t1,
+                                cudaStream_t stream);
+cudaError_t launch_h_shift(const double* hard_h, const double* q_h, const uint8_t* type_h, int nhp, double* d_new,
+                           const double* d_ref, KrylovScalars* sc, cudaStream_t stream);
+cudaError_t launch_set_identity_tiles(double* R, long ld, int nt, cudaStream_t stream);
+cudaError_t launch_krylov_finish(const double* A, long lda, int NP, int nxp, const double* sol, int nhp, double* v,
+                                 double* x, ScfState* state, cudaStream_t stream);
+cudaError_t launch_krylov_capture(const double* x, int nxp, int nhp, const ScfState* state, double* sol,
+                                  cudaStream_t stream);
 
 // ---- LU fallback (kernels_lu.cu) ------------------------------------------------------------------------------
 int lu_padded_size(int NP);

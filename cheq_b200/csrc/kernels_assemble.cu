@@ -34,13 +34,23 @@ __device__ __forceinline__ PairTableView rebase(PairTableView v, const char* fro
     return v;
 }
 
+// 1/sqrt(r2): CUDA's rsqrt (documented max error 1 ulp, not correctly rounded) plus ONE Newton step, after which
+// the result is within 0.51 ulp of the exact value -- as good as the reference's correctly rounded sqrt followed by a
+// divide (src/solver/implementation.rs:498-502; 0.5 + 0.5 ulp).  Three FMAs per pair; tests/test_gpu_parity.py
+// (test_pair_integrals_ulp_bound in tests/test_gpu_headline.py) pins |J_gpu - J_oracle| to a few ulp for both bases.
+__device__ __forceinline__ double rinv_refined(double r2) {
+    const double y = rsqrt(r2);
+    const double h = fma(-r2 * y, y, 1.0);       // 1 - r2 y^2
+    return fma(0.5 * y, h, y);
+}
+
 // J_eV for one pair of element types at squared distance r2 [Angstrom^2].
 template <int BASIS>
 __device__ __forceinline__ double pair_value(const PairTableView& tb, int ti, int tj, double r2) {
     const int p = ti * tb.num_types + tj;
     if (r2 < tb.rzero2[p]) return tb.j0[p];
-    // 1/R and R from one rsqrt (1 ulp) instead of sqrt + divide: the far-pair path is then store-bound
-    const double rinv = rsqrt(r2);
+    // 1/R and R from one refined rsqrt instead of sqrt + divide: the far-pair path is then store-bound
+    const double rinv = rinv_refined(r2);
     const double R = r2 * rinv;
     if (BASIS == 0) {
         // gto.rs:82-90: erf(beta R) / R
@@ -117,8 +127,8 @@ assemble_lower_kernel(AssembleArgs a, PairTableView view, const char* blob, int 
             // beyond every pair type's cutoff F(R) < 1e-19: J = kKe / R without touching the tables (with the
             // space-filling-curve order most warps take this branch as a whole)
             if (BASIS == 1 && r20 >= a.rcut2_max && r21 >= a.rcut2_max) {
-                v0 = (ti0 != kPadType) ? kKe * rsqrt(r20) : 0.0;
-                v1 = (ti1 != kPadType) ? kKe * rsqrt(r21) : 0.0;
+                v0 = (ti0 != kPadType) ? kKe * rinv_refined(r20) : 0.0;
+                v1 = (ti1 != kPadType) ? kKe * rinv_refined(r21) : 0.0;
             } else {
                 if (ti0 != kPadType) v0 = pair_value<BASIS>(tb, ti0, tjj, r20);
                 if (ti1 != kPadType) v1 = pair_value<BASIS>(tb, ti1, tjj, r21);

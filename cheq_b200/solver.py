@@ -52,6 +52,25 @@ class Context:
         self._lib.cheq_get_stats(self.handle, C.byref(s))
         return s.as_dict()
 
+    def scf_trace(self):
+        """Per SCF iteration of the last single-frame solve: (delta, mode, gmres_steps); mode 0 = the hydrogen block
+        was refactorised, 1 = frozen factor + GMRES."""
+        cap = 4096
+        d = (C.c_double * cap)()
+        m = (C.c_int32 * cap)()
+        k = (C.c_int32 * cap)()
+        cnt = C.c_uint32()
+        self._lib.cheq_get_scf_trace(self.handle, cap, d, m, k, C.byref(cnt))
+        n = min(cap, cnt.value)
+        return [(d[i], m[i], k[i]) for i in range(n)]
+
+    def set_krylov(self, enabled: bool = True, min_hydrogen: int = 0, freeze_ev: float = 0.0,
+                   force_iteration: int = 0):
+        rc = self._lib.cheq_set_krylov(self.handle, 1 if enabled else 0, int(min_hydrogen), float(freeze_ev),
+                                       int(force_iteration))
+        if rc != _ffi.OK:
+            raise CheqError(f"cheq_set_krylov failed with status {rc}")
+
 
 _default_ctx = {}
 _default_lock = threading.Lock()

@@ -142,6 +142,14 @@ def md_frames(base_xyz, n_frames: int, seed: int = SEED, sigma: float = 0.05):
     return out
 
 
+def md_frames_subset(base_xyz, indices, seed: int = SEED, sigma: float = 0.05):
+    """The frames `indices` of md_frames(base_xyz, ...) without generating the others (one rank's shard)."""
+    out = np.empty((len(indices),) + base_xyz.shape)
+    for k, f in enumerate(indices):
+        out[k] = base_xyz + np.random.default_rng(seed + int(f)).normal(scale=sigma, size=base_xyz.shape)
+    return out
+
+
 def water_20k(seed: int = SEED):
     """S20k: 6,667 waters = 20,001 atoms (the headline configuration)."""
     return water_cluster(6667, seed)

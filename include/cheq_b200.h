@@ -90,6 +90,12 @@ typedef struct cheq_stats {
     uint64_t gemm_launches;
     double potrf_ms;         /* same, diagonal-tile factorisation launches */
     double backsolve_ms;     /* same, whole back substitutions */
+    /* stale-factor SCF iterations: iterations solved by preconditioned GMRES on a frozen factor instead of a
+     * refactorisation of the hydrogen block, and the operator applications (one pass over S0 + two over R) they took */
+    uint64_t krylov_iterations;
+    uint64_t krylov_steps;
+    double krylov_ms;        /* device time of those iterations (CUDA events), incl. building R = L^-T S */
+    double krylov_bytes;     /* algorithmic bytes streamed by the tiled matrix-vector kernels in them */
 } cheq_stats;
 
 int32_t cheq_ctx_create(int32_t device, cheq_ctx** out);
@@ -101,6 +107,18 @@ int32_t cheq_get_stats(const cheq_ctx* ctx, cheq_stats* out);
 void* cheq_ctx_stream(const cheq_ctx* ctx);
 /* Per-launch CUDA-event timing of the dominant kernel (off by default; adds two event records per launch). */
 int32_t cheq_set_profiling(cheq_ctx* ctx, int32_t enabled);
+
+/* SCF trace of the last single-frame solve on this context: per iteration the max-abs charge change
+ * (implementation.rs:589-594), how the linear system was solved (0: hydrogen block refactorised, 1: frozen factor +
+ * GMRES) and the GMRES operator applications.  Arrays of `capacity` entries (each nullable); returns the number of
+ * iterations recorded in *count_out.  Used by the parity tests to compare the whole trajectory with the CPU path. */
+int32_t cheq_get_scf_trace(const cheq_ctx* ctx, uint32_t capacity, double* delta_out, int32_t* mode_out,
+                           int32_t* steps_out, uint32_t* count_out);
+/* Stale-factor policy.  enabled = 0 refactors the hydrogen block in every iteration (the
+ * round-1 behaviour); min_hydrogen: smallest hydrogen block that uses the frozen factor; freeze_ev: freeze once the
+ * largest change of the hydrogen diagonal between two iterations falls below this many eV; force_iteration: freeze at
+ * this SCF iteration at the latest.  Negative / zero values keep the current setting. */
+int32_t cheq_set_krylov(cheq_ctx* ctx, int32_t enabled, int32_t min_hydrogen, double freeze_ev, int32_t force_iteration);
 
 /* ---- multi-GPU: one dense system across the GPUs of a node ----------------------------
  * The reference is single-node CPU code (rayon, implementation.rs:394, 491) and has no equivalent; this is the

@@ -65,6 +65,8 @@ def lib():
         _LIB.cheq_oracle_build_system.restype = i64
         _LIB.cheq_oracle_build_system.argtypes = [i64, p, p, p, p, p, d, p, d, ctypes.c_int, p, p, p]
         _LIB.cheq_oracle_num_threads.restype = ctypes.c_int
+        _LIB.cheq_oracle_set_threads.restype = None
+        _LIB.cheq_oracle_set_threads.argtypes = [ctypes.c_int]
     return _LIB
 
 
@@ -230,3 +232,22 @@ def solve(Z, xyz, total_charge=0.0, opt: Options | None = None, params=None, ext
 
 def num_threads() -> int:
     return int(lib().cheq_oracle_num_threads())
+
+
+def use_all_cores() -> int:
+    """Give both halves of the CPU path every core this process may run on: the OpenMP assembly loops (the
+    reference's rayon loop) and the LAPACK LU behind scipy (the reference's faer).  Needed under launchers that
+    export OMP_NUM_THREADS=1 (torchrun).  Returns the core count."""
+    import os
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().cheq_oracle_set_threads(cores)
+    try:
+        from threadpoolctl import threadpool_limits
+        global _BLAS_LIMIT
+        _BLAS_LIMIT = threadpool_limits(limits=cores)      # stays in force for the life of the process
+    except Exception:
+        pass
+    return cores
+
+
+_BLAS_LIMIT = None

@@ -36,6 +36,8 @@ def main():
     ctx._lib.cheq_ctx_dist_info(ctx.handle, C.byref(r_), C.byref(w_))
     assert (r_.value, w_.value) == (rank, world)
     local_ctx = cheq_b200.Context(local) if rank == 0 else None   # plain single-GPU engine for comparisons
+    if local_ctx is not None:
+        local_ctx._lib.cheq_set_factor_mode(local_ctx.handle, 2, 0)   # recursive schedule, whatever the environment says
     P = get_default_parameters()
     big = int(os.environ.get("CHEQ_DIST_TEST_BIG", "2200"))
 
@@ -46,7 +48,7 @@ def main():
         assert torch.equal(t, ref), "ranks disagree"
 
     def run_case(name, Z, xyz, opts, ext=None, oracle_check=True, tpp=4, expect_fallback=None):
-        ctx._lib.cheq_set_factor_mode(ctx.handle, 0, tpp)
+        ctx._lib.cheq_set_factor_mode(ctx.handle, 1 if world == 1 else 0, tpp)
         chi, hard, rad, nq = workloads.gather_parameters(Z, P)
         s = QEqSolver(P, opts, ctx)
         res = s.solve_arrays(np.ascontiguousarray(xyz), chi, hard, rad, nq, 0.0, ext)
@@ -97,6 +99,22 @@ def main():
     fx = json.loads((ROOT / "tests" / "golden" / "rappe_goddard.json").read_text())
     c = [c for g in fx["groups"] for c in g["cases"] if c["name"] == "C2H4"][0]
     run_case("C2H4/indefinite", c["Z"], np.array(c["xyz"]), SolverOptions(), expect_fallback=0)
+    # batches on a JOINED context stay local whatever the shard size (a one-frame shard must not enter
+    # the collective factorisation): world + 1 frames -> rank 0 gets two frames, every other rank exactly one
+    from cheq_b200.parallel import solve_batch_sharded
+    Zm, base = workloads.organic_chain(200)
+    frames = workloads.md_frames(base, world + 1)
+    sb = QEqSolver(P, SolverOptions(), ctx)
+    qb, mub, itb, stb = solve_batch_sharded(lambda fr: sb.solve_batch(Zm, fr, 0.0), frames)
+    assert np.all(stb == 0)
+    if rank == 0:
+        from oracle import oracle as O
+        for f in range(len(frames)):
+            ref = O.solve(list(Zm), frames[f], 0.0)
+            assert itb[f] == ref.iterations and np.max(np.abs(qb[f] - ref.charges)) <= 1e-8, f
+        print(f"batch of {world + 1} frames on the joined contexts: per-frame oracle parity ok", flush=True)
+    # ... and the next collective solve still works afterwards
+    run_case("water750/after-batch", Z, xyz, SolverOptions(), tpp=2)
     # a larger system against the single-GPU engine
     Zb, xb = workloads.water_cluster(big)
     run_case(f"water{3 * big}", Zb, xb, SolverOptions(), oracle_check=False)

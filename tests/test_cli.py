@@ -113,3 +113,39 @@ def test_cheq_water_xyz_end_to_end(tmp_path, gpu_ctx, oracle):
     out2 = tmp_path / "traj.csv"
     assert cli.run([str(traj), "--trajectory", "-f", "csv", "-o", str(out2)]) == 0
     assert len(out2.read_text().splitlines()) == 3 * 4
+
+
+@pytest.mark.gpu
+def test_cli_field_and_point_charges_end_to_end(tmp_path, gpu_ctx, oracle):
+    """SURVEY section 8(f) row 4: `--field` and `--point-charges` drive QEqSolver::solve_in_field
+    (/root/reference/src/solver/implementation.rs:239-266) from the command line; result vs the CPU oracle."""
+    import numpy as np
+    from cheq_b200 import workloads
+    Z, xyz = workloads.water_cluster(27)
+    sym = {8: "O", 1: "H", 6: "C", 7: "N"}
+    f = tmp_path / "cluster.xyz"
+    f.write_text(f"{len(Z)}\ncluster\n" + "".join(f"{sym[z]} {p[0]:.10f} {p[1]:.10f} {p[2]:.10f}\n" for z, p in zip(Z, xyz)))
+    rng = np.random.default_rng(3)
+    pcZ = [8, 1, 7, 6, 1, 8]
+    pc_xyz = xyz.mean(axis=0) + rng.normal(size=(len(pcZ), 3)) * 3.0 + np.array([14.0, 0.0, 0.0])
+    pc_q = np.array([-0.6, 0.3, -0.2, 0.1, 0.3, 0.1])
+    pcf = tmp_path / "charges.txt"
+    pcf.write_text("".join(f"{sym[z]} {p[0]:.10f} {p[1]:.10f} {p[2]:.10f} {q:.10f}\n" for z, p, q in zip(pcZ, pc_xyz, pc_q)))
+    field = [0.05, -0.02, 0.1]
+    atoms, _ = cli.read_atoms(str(f))
+    axyz = np.array([a.position for a in atoms])
+    pcs = cli.read_point_charges(str(pcf))
+    ext = {"Z": [pc.atomic_number for pc in pcs], "xyz": np.array([pc.position for pc in pcs]),
+           "q": np.array([pc.charge for pc in pcs]), "field": field}
+    for args, e in ((["--field", *map(str, field)], {"Z": [], "xyz": np.zeros((0, 3)), "q": [], "field": field}),
+                    (["--point-charges", str(pcf)], dict(ext, field=[0.0, 0.0, 0.0])),
+                    (["--point-charges", str(pcf), "--field", *map(str, field)], ext)):
+        out = tmp_path / "out.json"
+        assert cli.run([str(f), "-f", "json", "-p", "10", "-o", str(out), *args]) == 0
+        doc = json.loads(out.read_text())
+        ref = oracle.solve(Z, axyz, 0.0, oracle.Options(max_iterations=100), external=e)
+        assert doc["iterations"] == ref.iterations
+        assert max(abs(a["charge"] - q) for a, q in zip(doc["atoms"], ref.charges)) < 1e-8
+        assert abs(doc["equilibrated_potential"] - ref.equilibrated_potential) < 1e-8
+    vac = oracle.solve(Z, axyz, 0.0, oracle.Options(max_iterations=100))
+    assert max(abs(a["charge"] - q) for a, q in zip(doc["atoms"], vac.charges)) > 1e-4   # the field really acts

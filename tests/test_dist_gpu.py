@@ -15,11 +15,17 @@ def _gpu_count():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [1, 2])
 def test_distributed_factorisation_parity(world):
+    """world = 1 runs the same worker on the single GPU of the driver's test box with the panel schedule forced
+    (CHEQ_FACTOR_MODE=1): the multi-GPU factorisation code path (right-looking panels, panel / bulk / main streams,
+    look-ahead events) without the NCCL exchange, which needs a second device."""
     if _gpu_count() < world:
         pytest.skip(f"needs {world} GPUs")
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    if world == 1:
+        env["CHEQ_FACTOR_MODE"] = "1"
+        env["CHEQ_DIST_TEST_BIG"] = "1200"
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", "29517", str(ROOT / "tests" / "dist_worker.py")]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=900, env=env)

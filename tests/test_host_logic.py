@@ -104,7 +104,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert C.sizeof(_ffi.Options) == 32
     assert C.sizeof(_ffi.External) == 8 + 4 * 8 + 24
-    assert C.sizeof(_ffi.Stats) == 7 * 8 + 4 * 8 + 2 * 4 + 2 * 8 + 8 + 5 * 8
+    assert C.sizeof(_ffi.Stats) == 7 * 8 + 4 * 8 + 2 * 4 + 2 * 8 + 8 + 5 * 8 + 4 * 8   # + the four krylov_* fields
     o = _ffi.Options()
     _ffi.lib().cheq_options_default(C.byref(o))
     assert (o.tolerance, o.lambda_scale, o.damping_value, o.max_iterations) == (1e-6, 0.5, 0.4, 2000)
@@ -171,6 +171,33 @@ def test_engine_algebra_model_matches_oracle(oracle, rg_fixtures):
         q, mu, it = solve_model(M[:n, :n].copy(), chi, hard, nq, 0.0)
         assert it == ref.iterations
         assert np.max(np.abs(q - ref.charges)) < 1e-12 and abs(mu - ref.equilibrated_potential) < 1e-12
+
+
+def test_stale_factor_model_matches_oracle(oracle, rg_fixtures):
+    """The stale-factor SCF iterations (frozen hydrogen factor + preconditioned GMRES on the reduced bordered system,
+    kernels_krylov.cu) follow the reference's trajectory: same iteration count, charges to 1e-11."""
+    from cheq_b200 import workloads as W
+    from engine_model import solve_model_stale
+    P = oracle.default_parameters()
+    cases = [(c["Z"], np.array(c["xyz"])) for g, c in rg_cases(rg_fixtures)
+             if sum(1 for z in c["Z"] if z in (1, 2)) >= 4][:6]
+    Zw, xw = W.water_cluster(60)
+    cases.append((Zw, xw))
+    Zo, xo = W.organic_chain(150)
+    cases.append((Zo, xo))
+    used = 0
+    for Z, xyz in cases:
+        chi, hard, rad, nq = oracle.gather(Z, P)
+        ref = oracle.solve(Z, xyz)
+        M, rhs, hidx = oracle.build_system(xyz, chi, hard, rad, nq, 0.0, None, oracle.Options())
+        n = len(chi)
+        trace = []
+        q, mu, it = solve_model_stale(M[:n, :n].copy(), chi, hard, nq, 0.0, trace=trace)
+        assert it == ref.iterations
+        assert np.max(np.abs(q - ref.charges)) < 1e-11 and abs(mu - ref.equilibrated_potential) < 1e-11
+        used += sum(m for m, _ in trace)
+        assert all(steps <= 40 for m, steps in trace if m)
+    assert used > 10   # the frozen-factor branch really ran
 
 
 def test_c2h4_fixture_is_indefinite(oracle, rg_fixtures):
