@@ -253,7 +253,8 @@ struct cheq_ctx {
     int morton = 1;                   // CHEQ_MORTON=0: atoms of one element stay in input order (test knob: a
                                       // different elimination order for the unpivoted factorisation)
     int krylov_mode = 1;              // CHEQ_KRYLOV=0: refactor the hydrogen block in every SCF iteration
-    int krylov_min_nhp = 1024;        // CHEQ_KRYLOV_MIN_NH: smallest padded hydrogen block that uses the stale factor
+    int krylov_min_nhp = 4096;        // CHEQ_KRYLOV_MIN_NH: smallest padded hydrogen block that uses the stale factor (B3k,
+                                      // nhp = 2048: 33.6 ms with it vs 23.7 ms without -- its GMRES steps are launch-latency-bound)
     double krylov_freeze_ev = 4.5;    // CHEQ_KRYLOV_FREEZE_EV: freeze once max |D_k - D_(k-1)| falls below this
     int krylov_force_it = 5;          // ... or at this SCF iteration at the latest
     struct TraceEntry { double delta; int mode; int steps; };   // mode 0: refactored, 1: stale factor + GMRES

@@ -96,6 +96,32 @@ cudaError_t launch_scatter_charges(int NP, const int* perm, const double* q, lon
 cudaError_t launch_export_matrix(int NP, long ld, const double* A, const int* perm, long n, double* out,
                                  cudaStream_t stream);
 
+// ---- matrix-free path (kernels_assemble.cu) -------------------------------------------------------------------
+struct MatfreeArgs {
+    const double *x, *y, *z;   // [NP] internal (Morton) order
+    const uint8_t* type;       // [NP], 255 = padding
+    const double* diag;        // [NP] hardness
+    const double* shift;       // [NP] nullable: charge-dependent diagonal shift of the n == 1 atoms
+    int NP;                    // padded atom count, multiple of 256
+    int row0, rows;            // this rank's row range (multiples of 128)
+    int slices;                // column slices per row tile (partials reduced in order)
+    const double* vin;         // [nv][vstride] input vectors: NP entries + the border unknown at index NP
+    double* out;               // [nv][vstride]
+    long vstride;
+    double* part;              // [slices][nv][rows]
+    double rcut2_max;
+    int table_smem_bytes;      // filled by the launcher
+};
+// out[rows of this rank] = (K v)[rows],  K = [[diag(hardness + shift) + J, e], [e^T, 0]]; nv = 1 or 2
+cudaError_t launch_matfree_matvec(const MatfreeArgs& a, int nv, const PairTableView& view, const char* blob,
+                                  int blob_bytes, cudaStream_t stream);
+cudaError_t launch_matfree_border(const MatfreeArgs& a, int nv, cudaStream_t stream);
+cudaError_t launch_residual(const double* rhs, const double* kv, double* out, int len, cudaStream_t stream);
+cudaError_t launch_assemble_diag_blocks(const MatfreeArgs& a, const PairTableView& view, const char* blob,
+                                        int blob_bytes, double* blocks, cudaStream_t stream);
+cudaError_t launch_block_jacobi_apply(const double* Minv, const double* sgn, const double* r, double* u, int NP,
+                                      int nv, long vstride, cudaStream_t stream);
+
 // ---- dense (kernels_dense.cu) ------------------------------------------------------------------------------
 cudaError_t launch_gemm_nt(const GemmArgs& g, int m_tiles, int n_tiles, int batch, cudaStream_t stream);
 cudaError_t launch_dmma_rate(double* out, int blocks, int threads, int iters, cudaStream_t stream);

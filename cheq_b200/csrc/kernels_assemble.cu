@@ -237,6 +237,213 @@ __global__ void export_matrix_kernel(int NP, long ld, const double* A, const int
     out[(long)oi + (long)oj * n] = v;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Matrix-free path (large N: the (N + 1)^2 matrix is never formed; SURVEY.md section 8(e) last row, App. E.4).
+// y_i = sum_{j != i} J(i, j) v_j for the rows [row0, row0 + 128 gridDim.x) with the J tiles recomputed on the fly
+// from the same device function as the assembly (pair_value).  CTA = 128 rows x one slice of the columns
+// (gridDim.y slices, partial sums reduced by matfree_reduce_kernel in a fixed order); columns are staged in tiles of
+// 256 (coordinates, types, up to two input vectors); thread (rp, cg) owns rows 2 rp, 2 rp + 1 and the 64 columns
+// cg * 64 .. + 63 of every staged tile.  FP64-ALU-bound: no matrix traffic at all.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMfRows = 128, kMfCols = 256, kMfThreads = 256;
+
+template <int BASIS, int NV>
+__global__ void __launch_bounds__(kMfThreads)
+matfree_matvec_kernel(MatfreeArgs a, PairTableView view, const char* blob, int blob_bytes) {
+    extern __shared__ __align__(16) char smem_raw[];
+    double* xj = (double*)smem_raw;
+    double* yj = xj + kMfCols;
+    double* zj = yj + kMfCols;
+    double* vj = zj + kMfCols;                    // [NV][kMfCols]
+    int* tj = (int*)(vj + NV * kMfCols);
+    char* tab_smem = (char*)(tj + kMfCols);
+    PairTableView tb = stage_tables(view, blob, blob_bytes, tab_smem, a.table_smem_bytes);
+    const int t = threadIdx.x;
+    const int rp = t & 63, cg = t >> 6;
+    const int i0 = a.row0 + blockIdx.x * kMfRows + 2 * rp;
+    const double xi0 = a.x[i0], yi0 = a.y[i0], zi0 = a.z[i0];
+    const double xi1 = a.x[i0 + 1], yi1 = a.y[i0 + 1], zi1 = a.z[i0 + 1];
+    const int ti0 = a.type[i0], ti1 = a.type[i0 + 1];
+    double acc0[NV], acc1[NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) acc0[v] = acc1[v] = 0.0;
+    // this CTA's slice of the column tiles
+    const int tiles = a.NP / kMfCols;
+    const int per = (tiles + gridDim.y - 1) / gridDim.y;
+    const int tile_begin = blockIdx.y * per, tile_end = min(tiles, tile_begin + per);
+    for (int ct = tile_begin; ct < tile_end; ++ct) {
+        __syncthreads();
+        {
+            const int j = ct * kMfCols + t;
+            xj[t] = a.x[j];
+            yj[t] = a.y[j];
+            zj[t] = a.z[j];
+            tj[t] = a.type[j];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) vj[v * kMfCols + t] = a.vin[(long)v * a.vstride + j];
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int c = 0; c < 64; ++c) {
+            const int jl = cg * 64 + c;
+            const int j = ct * kMfCols + jl;
+            const int tjj = tj[jl];
+            if (tjj == kPadType) continue;
+            const double dx0 = xi0 - xj[jl], dy0 = yi0 - yj[jl], dz0 = zi0 - zj[jl];
+            const double dx1 = xi1 - xj[jl], dy1 = yi1 - yj[jl], dz1 = zi1 - zj[jl];
+            const double r20 = dx0 * dx0 + dy0 * dy0 + dz0 * dz0, r21 = dx1 * dx1 + dy1 * dy1 + dz1 * dz1;
+            double v0 = 0.0, v1 = 0.0;
+            if (BASIS == 1 && r20 >= a.rcut2_max && r21 >= a.rcut2_max) {
+                v0 = kKe * rinv_refined(r20);
+                v1 = kKe * rinv_refined(r21);
+            } else {
+                if (j != i0 && ti0 != kPadType) v0 = pair_value<BASIS>(tb, ti0, tjj, r20);
+                if (j != i0 + 1 && ti1 != kPadType) v1 = pair_value<BASIS>(tb, ti1, tjj, r21);
+            }
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                const double xv = vj[v * kMfCols + jl];
+                acc0[v] = fma(v0, xv, acc0[v]);
+                acc1[v] = fma(v1, xv, acc1[v]);
+            }
+        }
+    }
+    // reduce the four column groups (fixed order), one partial per (slice, row)
+    __syncthreads();
+    double* red = (double*)smem_raw;                 // [4][128][NV]
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        red[(cg * kMfRows + 2 * rp) * NV + v] = (ti0 != kPadType) ? acc0[v] : 0.0;
+        red[(cg * kMfRows + 2 * rp + 1) * NV + v] = (ti1 != kPadType) ? acc1[v] : 0.0;
+    }
+    __syncthreads();
+    if (t < kMfRows) {
+        const long row = (long)blockIdx.x * kMfRows + t;            // row inside this rank's range
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            const double s = red[(0 * kMfRows + t) * NV + v] + red[(1 * kMfRows + t) * NV + v] +
+                             red[(2 * kMfRows + t) * NV + v] + red[(3 * kMfRows + t) * NV + v];
+            a.part[((long)blockIdx.y * NV + v) * a.rows + row] = s;
+        }
+    }
+}
+
+// y_i = sum_slices part + (diag_i + shift_i) v_i + nu e_i   for this rank's rows; e_i = 1 on real atoms, padding
+// rows are identity rows.  Written at absolute row positions of `out` (the ranks' pieces are all-gathered after).
+__global__ void __launch_bounds__(256)
+matfree_reduce_kernel(MatfreeArgs a, int nv, int slices) {
+    const int r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= a.rows) return;
+    const int i = a.row0 + r;
+    const bool pad = a.type[i] == kPadType;
+    for (int v = 0; v < nv; ++v) {
+        double s = 0.0;
+        for (int k = 0; k < slices; ++k) s += a.part[((long)k * nv + v) * a.rows + r];
+        const double xi = a.vin[(long)v * a.vstride + i];
+        const double nu = a.vin[(long)v * a.vstride + a.NP];
+        s = pad ? xi : s + (a.diag[i] + (a.shift ? a.shift[i] : 0.0)) * xi + nu;
+        a.out[(long)v * a.vstride + i] = s;
+    }
+}
+
+// border entry of K v: e . v over the real atoms (one CTA per vector, fixed order); optionally out = rhs - K v
+__global__ void __launch_bounds__(1024)
+matfree_border_kernel(MatfreeArgs a, int NP) {
+    __shared__ double red[32];
+    const int v = blockIdx.x;
+    const double* x = a.vin + (long)v * a.vstride;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < NP; i += 1024)
+        if (a.type[i] != kPadType) s += x[i];
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int w = 0; w < 32; ++w) tot += red[w];
+        a.out[(long)v * a.vstride + NP] = tot;
+    }
+}
+
+// out = rhs - kv (n + 1 entries), used for true residuals
+__global__ void __launch_bounds__(256)
+axpby_residual_kernel(const double* rhs, const double* kv, double* out, int len) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < len) out[i] = rhs[i] - kv[i];
+}
+
+// 128 x 128 diagonal blocks of A = diag(hardness) + J for the block-Jacobi preconditioner: blocks[b] column-major,
+// ld 128, both triangles (the factorisation reads the lower one).  One CTA per block.
+template <int BASIS>
+__global__ void __launch_bounds__(256)
+assemble_diag_blocks_kernel(MatfreeArgs a, PairTableView view, const char* blob, int blob_bytes, double* blocks) {
+    extern __shared__ __align__(16) char smem_raw[];
+    double* xj = (double*)smem_raw;
+    double* yj = xj + kTile;
+    double* zj = yj + kTile;
+    int* tj = (int*)(zj + kTile);
+    char* tab_smem = (char*)(tj + kTile);
+    const int b = blockIdx.x, t = threadIdx.x;
+    if (t < kTile) {
+        const int j = b * kTile + t;
+        xj[t] = a.x[j];
+        yj[t] = a.y[j];
+        zj[t] = a.z[j];
+        tj[t] = a.type[j];
+    }
+    PairTableView tb = stage_tables(view, blob, blob_bytes, tab_smem, a.table_smem_bytes);
+    __syncthreads();
+    double* out = blocks + (long)b * kTile * kTile;
+    for (int idx = t; idx < kTile * kTile; idx += 256) {
+        const int r = idx & (kTile - 1), c = idx >> 7;
+        const int tr = tj[r], tc = tj[c];
+        double v;
+        if (r == c) {
+            v = (tr == kPadType) ? 1.0 : a.diag[b * kTile + r];
+        } else if (tr == kPadType || tc == kPadType) {
+            v = 0.0;
+        } else {
+            const double dx = xj[r] - xj[c], dy = yj[r] - yj[c], dz = zj[r] - zj[c];
+            v = pair_value<BASIS>(tb, tr, tc, dx * dx + dy * dy + dz * dz);
+        }
+        out[idx] = v;
+    }
+}
+
+// u_b = M_b^T S_b M_b r_b  (= A_b^-1 r_b with A_b = L S L^T, M = S L^-1) for every 128-block: M staged in shared
+// memory (padded), two triangular products.
+constexpr int kBjLd = kTile + 1;
+__global__ void __launch_bounds__(256)
+block_jacobi_apply_kernel(const double* Minv, const double* sgn, const double* r, double* u, int nv, long vstride) {
+    extern __shared__ __align__(16) double Ms[];    // [128][129]
+    __shared__ double tv[2][kTile];
+    const int b = blockIdx.x, t = threadIdx.x;
+    const double* M = Minv + (long)b * kTile * kTile;
+    for (int idx = t; idx < kTile * kTile; idx += 256) {
+        const int i = idx & (kTile - 1), j = idx >> 7;            // M[i][j], column-major in global memory
+        Ms[i * kBjLd + j] = M[idx];
+    }
+    __syncthreads();
+    for (int v = 0; v < nv; ++v) {
+        const double* rb = r + (long)v * vstride + (long)b * kTile;
+        if (t < kTile) tv[0][t] = rb[t];
+        __syncthreads();
+        if (t < kTile) {                       // t_i = s_i sum_{j <= i} M[i][j] r_j
+            double s = 0.0;
+            for (int j = 0; j <= t; ++j) s = fma(Ms[t * kBjLd + j], tv[0][j], s);
+            tv[1][t] = sgn[(long)b * kTile + t] * s;
+        }
+        __syncthreads();
+        if (t < kTile) {                       // u_j = sum_{i >= j} M[i][j] t_i
+            double s = 0.0;
+            for (int i = t; i < kTile; ++i) s = fma(Ms[i * kBjLd + t], tv[1][i], s);
+            u[(long)v * vstride + (long)b * kTile + t] = s;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 int assemble_smem_bytes(int table_bytes, int* table_smem_bytes) {
@@ -306,6 +513,69 @@ cudaError_t launch_export_matrix(int NP, long ld, const double* A, const int* pe
                                  cudaStream_t stream) {
     dim3 grid(NP, (NP + 255) / 256, 1);
     export_matrix_kernel<<<grid, 256, 0, stream>>>(NP, ld, A, perm, n, out);
+    return cudaGetLastError();
+}
+
+
+cudaError_t launch_matfree_matvec(const MatfreeArgs& a, int nv, const PairTableView& view, const char* blob,
+                                  int blob_bytes, cudaStream_t stream) {
+    MatfreeArgs args = a;
+    const int budget = 96 * 1024;
+    args.table_smem_bytes = (blob_bytes <= budget) ? ((blob_bytes + 15) / 16) * 16 : 0;
+    const int stage = kMfCols * (3 + nv) * (int)sizeof(double) + kMfCols * (int)sizeof(int);
+    const int red = 4 * kMfRows * nv * (int)sizeof(double);
+    const int smem = (stage > red ? stage : red) + args.table_smem_bytes;
+    // the table blob sits behind the staging area: make sure the reduction scratch does not reach into it
+    const int base = stage > red ? stage : red;
+    (void)base;
+    dim3 grid(a.rows / kMfRows, a.slices);
+    cudaError_t e;
+    if (nv == 1) {
+        auto kern = view.basis == 0 ? matfree_matvec_kernel<0, 1> : matfree_matvec_kernel<1, 1>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, kMfThreads, smem, stream>>>(args, view, blob, blob_bytes);
+    } else {
+        auto kern = view.basis == 0 ? matfree_matvec_kernel<0, 2> : matfree_matvec_kernel<1, 2>;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, kMfThreads, smem, stream>>>(args, view, blob, blob_bytes);
+    }
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    matfree_reduce_kernel<<<(a.rows + 255) / 256, 256, 0, stream>>>(args, nv, a.slices);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_matfree_border(const MatfreeArgs& a, int nv, cudaStream_t stream) {
+    matfree_border_kernel<<<nv, 1024, 0, stream>>>(a, a.NP);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_residual(const double* rhs, const double* kv, double* out, int len, cudaStream_t stream) {
+    axpby_residual_kernel<<<(len + 255) / 256, 256, 0, stream>>>(rhs, kv, out, len);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_assemble_diag_blocks(const MatfreeArgs& a, const PairTableView& view, const char* blob,
+                                        int blob_bytes, double* blocks, cudaStream_t stream) {
+    MatfreeArgs args = a;
+    const int budget = 96 * 1024;
+    args.table_smem_bytes = (blob_bytes <= budget) ? ((blob_bytes + 15) / 16) * 16 : 0;
+    const int smem = kTile * 3 * (int)sizeof(double) + kTile * (int)sizeof(int) + args.table_smem_bytes;
+    auto kern = view.basis == 0 ? assemble_diag_blocks_kernel<0> : assemble_diag_blocks_kernel<1>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    kern<<<a.NP / kTile, 256, smem, stream>>>(args, view, blob, blob_bytes, blocks);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_block_jacobi_apply(const double* Minv, const double* sgn, const double* r, double* u, int NP,
+                                      int nv, long vstride, cudaStream_t stream) {
+    const int smem = kTile * kBjLd * (int)sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(block_jacobi_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    block_jacobi_apply_kernel<<<NP / kTile, 256, smem, stream>>>(Minv, sgn, r, u, nv, vstride);
     return cudaGetLastError();
 }
 
