@@ -33,7 +33,7 @@ class Stats(C.Structure):
                 ("lu_fallback_frames", C.c_uint64), ("gemm_ms", C.c_double), ("gemm_flops", C.c_double),
                 ("gemm_launches", C.c_uint64), ("potrf_ms", C.c_double), ("backsolve_ms", C.c_double),
                 ("krylov_iterations", C.c_uint64), ("krylov_steps", C.c_uint64), ("krylov_ms", C.c_double),
-                ("krylov_bytes", C.c_double)]
+                ("krylov_bytes", C.c_double), ("matfree_matvecs", C.c_uint64), ("matfree_pairs", C.c_double)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -58,6 +58,8 @@ SIGNATURES = {
     "cheq_dist_plan": (_I32, [_I32, _I32, _I32, _I32, _P, _P]),
     "cheq_solve": (_I32, [_P, _U64, _P, _P, _P, _P, _P, _D, C.POINTER(Options), C.POINTER(External), _P,
                           C.POINTER(_D), C.POINTER(C.c_uint32), C.POINTER(_D)]),
+    "cheq_solve_iterative": (_I32, [_P, _U64, _P, _P, _P, _P, _P, _D, C.POINTER(Options), C.POINTER(External), _P,
+                                    C.POINTER(_D), C.POINTER(C.c_uint32), C.POINTER(_D)]),
     "cheq_solve_device": (_I32, [_P, _U64, _P, _P, _P, _P, _P, _D, C.POINTER(Options), C.POINTER(External), _P,
                                  C.POINTER(_D), C.POINTER(C.c_uint32), C.POINTER(_D)]),
     "cheq_solve_batch": (_I32, [_P, _U64, _U64, _P, _P, _P, _P, _P, _D, C.POINTER(Options), _P, _P, _P, _P, _P]),

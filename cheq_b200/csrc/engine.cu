@@ -199,8 +199,16 @@ struct NcclApi {
 };
 constexpr int kNcclChar = 0, kNcclInt = 2, kNcclDouble = 8, kNcclMax = 2;
 
+struct MatfreeBuffers {
+    DeviceBuffer vec, part, blocks, minv, sgn, hflag, basis;
+    void release() {
+        for (DeviceBuffer* b : {&vec, &part, &blocks, &minv, &sgn, &hflag, &basis}) b->release();
+    }
+};
+
 struct cheq_ctx {
     int device = 0;
+    MatfreeBuffers* mf = nullptr;          // workspace of the matrix-free path (allocated on first use)
     cudaStream_t stream = nullptr;
     cudaStream_t cur = nullptr;            // stream the factorisation kernels are launched on (stream or panel_stream)
     // distributed / look-ahead factorisation
@@ -257,7 +265,10 @@ struct cheq_ctx {
                                       // nhp = 2048: 33.6 ms with it vs 23.7 ms without -- its GMRES steps are launch-latency-bound)
     double krylov_freeze_ev = 4.5;    // CHEQ_KRYLOV_FREEZE_EV: freeze once max |D_k - D_(k-1)| falls below this
     int krylov_force_it = 5;          // ... or at this SCF iteration at the latest
-    struct TraceEntry { double delta; int mode; int steps; };   // mode 0: refactored, 1: stale factor + GMRES
+    int matfree_restart = 160;        // CHEQ_MATFREE_RESTART: GMRES restart length of the matrix-free path
+    int matfree_max_steps = 4000;     // CHEQ_MATFREE_MAX_STEPS: operator applications per SCF iteration
+    double matfree_tol = 1e-12;       // CHEQ_MATFREE_TOL: |P (b - K x)| <= tol |x|
+    struct TraceEntry { double delta; int mode; int steps; };   // mode 0: refactored, 1: stale factor + GMRES, 2: matrix-free GMRES
     std::vector<TraceEntry> trace;    // per SCF iteration of the last single-frame solve
     ScfState* h_state = nullptr;   // pinned
     int* h_active = nullptr;       // pinned
@@ -351,7 +362,7 @@ uint32_t morton30(double fx, double fy, double fz) {
 
 int make_layout(cheq_ctx* ctx, long n, const double* radius, const uint8_t* nq, bool hydrogen_scf,
                 const double* pc_radius, const uint8_t* pc_n, long m, const double* xyz, Layout& L,
-                std::vector<int>& pc_type) {
+                std::vector<int>& pc_type, int spatial_pad = 0) {
     L.n = n;
     std::map<std::pair<uint8_t, uint64_t>, int> index;
     std::vector<int> atom_type(n);
@@ -365,11 +376,11 @@ int make_layout(cheq_ctx* ctx, long n, const double* radius, const uint8_t* nq, 
     std::vector<int> xs, hs;
     xs.reserve(n);
     for (long i = 0; i < n; ++i) {
-        if (L.scf && nq[i] == 1) hs.push_back((int)i);
+        if (L.scf && nq[i] == 1 && !spatial_pad) hs.push_back((int)i);
         else xs.push_back((int)i);
     }
     std::vector<uint32_t> code(n, 0);
-    if (xyz && n > 256 && ctx->morton) {
+    if (xyz && (spatial_pad || (n > 256 && ctx->morton))) {
         double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
         for (long i = 0; i < n; ++i)
             for (int d = 0; d < 3; ++d) {
@@ -382,7 +393,9 @@ int make_layout(cheq_ctx* ctx, long n, const double* radius, const uint8_t* nq, 
             code[i] = morton30((xyz[3 * i] - lo[0]) / ext, (xyz[3 * i + 1] - lo[1]) / ext, (xyz[3 * i + 2] - lo[2]) / ext);
     }
     auto by_type = [&](int a, int b) {
-        if (atom_type[a] != atom_type[b]) return atom_type[a] < atom_type[b];
+        // matrix-free path (spatial_pad): one block, pure space-filling-curve order, so that 128 consecutive atoms
+        // are a compact cluster of whole molecules (the block-Jacobi preconditioner's blocks)
+        if (!spatial_pad && atom_type[a] != atom_type[b]) return atom_type[a] < atom_type[b];
         if (code[a] != code[b]) return code[a] < code[b];
         return a < b;
     };
@@ -392,6 +405,7 @@ int make_layout(cheq_ctx* ctx, long n, const double* radius, const uint8_t* nq, 
     L.nh = (int)hs.size();
     L.nxp = round_up_tile(L.nx);
     L.nhp = round_up_tile(L.nh);
+    if (spatial_pad) L.nxp = (int)(((long)L.nx + spatial_pad - 1) / spatial_pad * spatial_pad);
     L.NP = L.nxp + L.nhp;
     L.MT = L.NP + kRhsRows;
     L.ld = L.MT;
@@ -1409,34 +1423,51 @@ int krylov_freeze(cheq_ctx* ctx, Dense& D, Krylov& K, int nxp, const double* d_o
     return CHEQ_OK;
 }
 
-// Solves K_k sol = [t_c; Q - h] with GMRES preconditioned by the frozen K_s^-1, restarted from the true residual
-// until the preconditioned residual (an estimate of the error itself) is below tol * |sol|.  `sol` holds the
-// previous iteration's solution on entry.  Returns the operator applications in *steps; *ok = false if it did not
-// get there (the caller then refactors).
-int krylov_solve(cheq_ctx* ctx, Krylov& K, double tol, int* steps, bool* ok) {
+// Restarted GMRES with iterative refinement, host-driven: the device does the operator / preconditioner applications
+// and the Gram-Schmidt arithmetic (classical, twice; fixed summation order), the host keeps the small Hessenberg
+// least-squares problem and reads one column of coefficients per step.  Left-preconditioned: the monitored quantity
+// |P (b - K x)| estimates the error itself when P ~ K^-1.  Every restart begins from the TRUE residual, and the solve
+// only ends when that (not the recurrence's estimate) is below tol * |sol_0|.
+struct GmresWork {
+    int len = 0;                 // entries per vector (unknowns + border)
+    long vs = 0;                 // vector stride in doubles
+    int m = 48;                  // restart length (<= kGmresMaxBasis)
+    int max_steps = 96;          // operator applications before giving up
+    double *r = nullptr, *z = nullptr, *w = nullptr, *V = nullptr;   // device: residual, P r, work vector, basis [m][vs]
+    KrylovScalars* sc = nullptr; // device
+    double stall_accept = 1e3;   // a stalled restart is accepted if |P r| <= stall_accept * tol * scale
+};
+
+template <class ApplyK, class ApplyP>
+int gmres_solve(cheq_ctx* ctx, const GmresWork& G, ApplyK&& apply_K, ApplyP&& apply_P, const double* rhs, double* sol,
+                double tol, int* steps, bool* ok) {
     cudaStream_t st = ctx->stream;
     KrylovScalars* hs = ctx->h_ksc;
-    constexpr int m = Krylov::kMaxBasis;
-    static thread_local double H[(m + 1) * m];
-    double cs[m], sn[m], gv[m + 1], y[m];
+    const int m = G.m;
+    constexpr int kNormSlot = kGmresMaxBasis + 1;
+    std::vector<double> H((size_t)(m + 1) * m), cs(m), sn(m), gv(m + 1), y(m);
     *steps = 0;
     *ok = false;
     static const bool debug = [] { const char* e = getenv("CHEQ_KRYLOV_DEBUG"); return e && e[0] == '1'; }();
     double scale = 0.0, beta_prev = 0.0;
-    for (int cycle = 0; cycle < 8; ++cycle) {
-        // true residual, preconditioned: z = K_s^-1 (b - K_k sol)
-        int rc = krylov_apply_K(ctx, K, K.sol, K.r, 2);
+    for (int cycle = 0; cycle < 64; ++cycle) {
+        // true residual, preconditioned: z = P (b - K sol)
+        int rc = apply_K(sol, G.r);
         if (rc) return rc;
-        rc = krylov_apply_precond(ctx, K, K.r, K.z);
+        LAUNCH(launch_residual(rhs, G.r, G.r, G.len, st));
+        rc = apply_P(G.r, G.z);
         if (rc) return rc;
         *steps += 1;
-        LAUNCH(launch_multi_dot(nullptr, 0, K.z, K.len, K.sc->dots, 0, true, st));
-        if (cycle == 0) LAUNCH(launch_multi_dot(nullptr, 0, K.sol, K.len, K.sc->dots + 1, 0, true, st));
-        CU(cudaMemcpyAsync(hs->dots, K.sc->dots, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        LAUNCH(launch_multi_dot(nullptr, 0, G.z, G.len, G.sc->dots, 0, true, st));
+        if (cycle == 0) LAUNCH(launch_multi_dot(nullptr, 0, sol, G.len, G.sc->dots + 1, 0, true, st));
+        CU(cudaMemcpyAsync(hs->dots, G.sc->dots, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
         const double beta = std::sqrt(hs->dots[0]);
-        if (cycle == 0) scale = std::max(std::sqrt(hs->dots[1]), 1e-300);
-        if (debug) fprintf(stderr, "[krylov] cycle %d steps %d  |P r| = %.3e  |sol| = %.3e\n", cycle, *steps, beta, scale);
+        if (cycle == 0) {
+            scale = std::sqrt(hs->dots[1]);
+            if (!(scale > 0.0)) scale = std::max(beta, 1e-300);   // zero initial guess: measure against the first correction
+        }
+        if (debug) fprintf(stderr, "[gmres] cycle %d steps %d  |P r| = %.3e  scale = %.3e\n", cycle, *steps, beta, scale);
         if (!std::isfinite(beta)) return CHEQ_OK;                        // not ok
         if (beta <= tol * scale) {
             *ok = true;
@@ -1444,64 +1475,83 @@ int krylov_solve(cheq_ctx* ctx, Krylov& K, double tol, int* steps, bool* ok) {
         }
         if (cycle > 0 && beta > 0.25 * beta_prev) {
             // rounding floor of this system (or a stalled restart): accept only if it is far below the parity budget
-            *ok = beta <= 1e3 * tol * scale;
+            *ok = beta <= G.stall_accept * tol * scale;
             return CHEQ_OK;
         }
-        if (*steps >= Krylov::kMaxSteps) return CHEQ_OK;
+        if (*steps >= G.max_steps) return CHEQ_OK;
         beta_prev = beta;
-        LAUNCH(launch_scale_by_rnorm(K.z, K.V, K.len, K.sc->dots, st));
+        LAUNCH(launch_scale_by_rnorm(G.z, G.V, G.len, G.sc->dots, st));
         gv[0] = beta;
         int k = 0;
         for (int j = 0; j < m; ++j) {
-            const double* vj = K.V + (long)j * K.vs;
-            rc = krylov_apply_K(ctx, K, vj, K.r, 1);
+            const double* vj = G.V + (long)j * G.vs;
+            rc = apply_K(vj, G.r);
             if (rc) return rc;
-            rc = krylov_apply_precond(ctx, K, K.r, K.w);
+            rc = apply_P(G.r, G.w);
             if (rc) return rc;
             *steps += 1;
             // classical Gram-Schmidt, twice
-            LAUNCH(launch_multi_dot(K.V, K.vs, K.w, K.len, K.sc->dots, j + 1, false, st));
-            LAUNCH(launch_gs_update(K.V, K.vs, K.w, K.len, K.sc->dots, K.sc->hsum, j + 1, true, st));
-            LAUNCH(launch_multi_dot(K.V, K.vs, K.w, K.len, K.sc->dots, j + 1, false, st));
-            LAUNCH(launch_gs_update(K.V, K.vs, K.w, K.len, K.sc->dots, K.sc->hsum, j + 1, false, st));
-            LAUNCH(launch_multi_dot(nullptr, 0, K.w, K.len, K.sc->dots + (m + 8), 0, true, st));
-            CU(cudaMemcpyAsync(hs->hsum, K.sc->hsum, (j + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(hs->dots + (m + 8), K.sc->dots + (m + 8), sizeof(double), cudaMemcpyDeviceToHost, st));
+            LAUNCH(launch_multi_dot(G.V, G.vs, G.w, G.len, G.sc->dots, j + 1, false, st));
+            LAUNCH(launch_gs_update(G.V, G.vs, G.w, G.len, G.sc->dots, G.sc->hsum, j + 1, true, st));
+            LAUNCH(launch_multi_dot(G.V, G.vs, G.w, G.len, G.sc->dots, j + 1, false, st));
+            LAUNCH(launch_gs_update(G.V, G.vs, G.w, G.len, G.sc->dots, G.sc->hsum, j + 1, false, st));
+            LAUNCH(launch_multi_dot(nullptr, 0, G.w, G.len, G.sc->dots + kNormSlot, 0, true, st));
+            CU(cudaMemcpyAsync(hs->hsum, G.sc->hsum, (j + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(hs->dots + kNormSlot, G.sc->dots + kNormSlot, sizeof(double), cudaMemcpyDeviceToHost, st));
             if (j + 1 < m)
-                LAUNCH(launch_scale_by_rnorm(K.w, K.V + (long)(j + 1) * K.vs, K.len, K.sc->dots + (m + 8), st));
+                LAUNCH(launch_scale_by_rnorm(G.w, G.V + (long)(j + 1) * G.vs, G.len, G.sc->dots + kNormSlot, st));
             CU(cudaStreamSynchronize(st));
-            for (int i = 0; i <= j; ++i) H[i * m + j] = hs->hsum[i];
-            double hn = std::sqrt(std::max(0.0, hs->dots[m + 8]));
+            for (int i = 0; i <= j; ++i) H[(size_t)i * m + j] = hs->hsum[i];
+            const double hn = std::sqrt(std::max(0.0, hs->dots[kNormSlot]));
             for (int i = 0; i < j; ++i) {
-                const double a = cs[i] * H[i * m + j] + sn[i] * H[(i + 1) * m + j];
-                H[(i + 1) * m + j] = -sn[i] * H[i * m + j] + cs[i] * H[(i + 1) * m + j];
-                H[i * m + j] = a;
+                const double a = cs[i] * H[(size_t)i * m + j] + sn[i] * H[(size_t)(i + 1) * m + j];
+                H[(size_t)(i + 1) * m + j] = -sn[i] * H[(size_t)i * m + j] + cs[i] * H[(size_t)(i + 1) * m + j];
+                H[(size_t)i * m + j] = a;
             }
-            const double rr = std::hypot(H[j * m + j], hn);
+            const double rr = std::hypot(H[(size_t)j * m + j], hn);
             if (!(rr > 0.0) || !std::isfinite(rr)) {
                 k = j;
                 break;
             }
-            cs[j] = H[j * m + j] / rr;
+            cs[j] = H[(size_t)j * m + j] / rr;
             sn[j] = hn / rr;
-            H[j * m + j] = rr;
+            H[(size_t)j * m + j] = rr;
             gv[j + 1] = -sn[j] * gv[j];
             gv[j] = cs[j] * gv[j];
             k = j + 1;
-            if (debug) fprintf(stderr, "[krylov]   step %d  estimate %.3e\n", j, std::fabs(gv[j + 1]));
-            if (std::fabs(gv[j + 1]) <= 0.3 * tol * scale || *steps >= Krylov::kMaxSteps) break;
+            if (debug) fprintf(stderr, "[gmres]   step %d  estimate %.3e\n", j, std::fabs(gv[j + 1]));
+            if (std::fabs(gv[j + 1]) <= 0.3 * tol * scale || *steps >= G.max_steps) break;
         }
         if (k == 0) return CHEQ_OK;
         for (int i = k - 1; i >= 0; --i) {
             double sacc = gv[i];
-            for (int c = i + 1; c < k; ++c) sacc -= H[i * m + c] * y[c];
-            y[i] = sacc / H[i * m + i];
+            for (int c = i + 1; c < k; ++c) sacc -= H[(size_t)i * m + c] * y[c];
+            y[i] = sacc / H[(size_t)i * m + i];
         }
         for (int i = 0; i < k; ++i) hs->y[i] = y[i];
-        CU(cudaMemcpyAsync(K.sc->y, hs->y, k * sizeof(double), cudaMemcpyHostToDevice, st));
-        LAUNCH(launch_combine(K.V, K.vs, K.sol, K.len, K.sc->y, k, st));
+        CU(cudaMemcpyAsync(G.sc->y, hs->y, k * sizeof(double), cudaMemcpyHostToDevice, st));
+        LAUNCH(launch_combine(G.V, G.vs, sol, G.len, G.sc->y, k, st));
     }
     return CHEQ_OK;
+}
+
+// Solves K_k sol = [t_c; Q - h] with GMRES preconditioned by the frozen K_s^-1.  `sol` holds the previous
+// iteration's solution on entry.  Returns the operator applications in *steps; *ok = false if it did not get there
+// (the caller then refactors).
+int krylov_solve(cheq_ctx* ctx, Krylov& K, double tol, int* steps, bool* ok) {
+    GmresWork G;
+    G.len = K.len;
+    G.vs = K.vs;
+    G.m = Krylov::kMaxBasis;
+    G.max_steps = Krylov::kMaxSteps;
+    G.r = K.r;
+    G.z = K.z;
+    G.w = K.w;
+    G.V = K.V;
+    G.sc = K.sc;
+    return gmres_solve(
+        ctx, G, [&](const double* v, double* out) { return krylov_apply_K(ctx, K, v, out, 1); },
+        [&](const double* in, double* out) { return krylov_apply_precond(ctx, K, in, out); }, K.tc, K.sol, tol, steps, ok);
 }
 
 int ensure_host_state(cheq_ctx* ctx, size_t batch) {
@@ -1531,6 +1581,7 @@ struct SolveIO {
     // (every rank calls them with identical inputs).  cheq_solve_batch and the component entry points are always
     // local, whatever the chunk size: a one-frame chunk of a batch must never enter the group's factorisation.
     bool collective = false;
+    int path = 0;   // 0: dense direct solve, matrix-free only if the matrix cannot fit; 1: dense; 2: matrix-free
 };
 
 int validate_options(cheq_ctx* ctx, const cheq_options* o) {
@@ -2112,6 +2163,263 @@ int emit_results(cheq_ctx* ctx, const SolveIO& io, const Prepared& P, long gf0, 
     return CHEQ_OK;
 }
 
+
+// ---- matrix-free path --------------------------------------------------------------------------------------------
+// QEqSolver::solve for systems whose (N + 1)^2 matrix does not fit (SURVEY.md section 8(e) last row, App. E.4).  The
+// reference holds three dense copies of it (implementation.rs:464, 282, 575); here it is never formed:
+//   K(q) [x; mu] = [c; Q],  K = [[diag(hardness + D(q)) + J, e], [e^T, 0]]
+// is solved in every SCF iteration by restarted GMRES (the matrix is symmetric but indefinite, DESIGN.md section 5.2,
+// so CG does not apply), K v recomputes the J tiles on the fly from the same device function as the assembly, rows
+// sharded over the ranks of the group with one ncclAllGather of the result per application (the Krylov vectors are
+// replicated, so dot products need no collective and all ranks stay bit-identical).  Preconditioner: block-Jacobi over
+// 128-atom blocks of the space-filling-curve order (compact clusters of whole molecules), each block factorised
+// A_b = L S L^T by the diagonal-tile kernel of the dense path, applied as M^T S M with M = S L^-1, border eliminated
+// exactly as in the stale-factor iterations.  Measured on the CPU model (tools/exp_matrix_free.py): 103 / 107 / 159
+// GMRES steps to 1e-12 at 3k / 8k / 20k atoms.
+
+int solve_matfree(cheq_ctx* ctx, const SolveIO& io) {
+    const long n = io.n;
+    const cheq_options& o = *io.opt;
+    cudaStream_t st = ctx->stream;
+    const int world = ctx->world, rank = ctx->rank;
+    const bool has_ext = !external_is_empty(io.ext);
+    const long m = has_ext ? (long)io.ext->num_point_charges : 0;
+    auto t_host = Clock::now();
+    if (io.device_ptrs) return fail(ctx, CHEQ_ERR_INVALID_ARGUMENT, "the matrix-free path takes host pointers");
+
+    // layout (pure Morton order, padded so that every rank owns a whole number of 128-row tiles and the column tiles
+    // of 256 divide NP), tables
+    Layout L;
+    std::vector<int> pc_type;
+    const int pad = 256 * world;
+    int rc = make_layout(ctx, n, io.radius, io.nq, o.hydrogen_scf != 0, has_ext ? io.ext->radius : nullptr,
+                         has_ext ? io.ext->n : nullptr, m, io.xyz, L, pc_type, pad);
+    if (rc) return rc;
+    const int NP = L.NP;
+    PackedTables pk;
+    rc = pack_tables(ctx, L.types, o.lambda_scale, o.basis, pk);
+    if (rc) return rc;
+    PairTableView view;
+    rc = upload_tables(ctx, pk, view);
+    if (rc) return rc;
+    const int blob_bytes = (int)pk.blob.size();
+    const double rcut2_max = (o.basis == CHEQ_BASIS_STO) ? pk.rcut2_max : INFINITY;
+    std::vector<uint8_t> hflag(NP, 0);
+    for (int i = 0; i < NP; ++i)
+        if (L.perm[i] >= 0 && L.scf && io.nq[L.perm[i]] == 1) hflag[i] = 1;
+    ctx->stats.n_atoms = n;
+    ctx->stats.n_hydrogen = 0;
+    for (uint8_t f : hflag) ctx->stats.n_hydrogen += f;
+    ctx->stats.n_padded = NP;
+    ctx->stats.pair_types = pk.pair_types;
+
+    // device workspace
+    if (!ctx->mf) ctx->mf = new MatfreeBuffers();
+    MatfreeBuffers& MB = *ctx->mf;
+    const int restart = std::min(kGmresMaxBasis, std::max(32, ctx->matfree_restart));
+    const long vs = NP + 8;
+    const int nb = NP / kTile;
+    const int rows = NP / world, row0 = rank * rows;
+    int slices = 1;
+    while ((rows / kTile) * slices < 4 * 148 && slices < NP / 256) slices *= 2;
+    CU(ctx->perm.ensure((size_t)NP * sizeof(int)));
+    CU(ctx->type.ensure(NP));
+    const size_t vec = (size_t)NP * 8;
+    CU(ctx->x.ensure(vec));
+    CU(ctx->y.ensure(vec));
+    CU(ctx->z.ensure(vec));
+    CU(ctx->q.ensure(vec));
+    CU(ctx->xsol.ensure(vec));
+    CU(ctx->diag.ensure(vec));
+    CU(ctx->chi.ensure(vec));
+    CU(ctx->hard.ensure(vec));
+    CU(ctx->state.ensure(sizeof(ScfState)));
+    CU(ctx->active.ensure(sizeof(int)));
+    CU(ctx->kr_sc.ensure(sizeof(KrylovScalars)));
+    if (!ctx->h_ksc) CU(cudaMallocHost((void**)&ctx->h_ksc, sizeof(KrylovScalars)));
+    rc = ensure_host_state(ctx, 1);
+    if (rc) return rc;
+    if (!ctx->h_active) CU(cudaMallocHost((void**)&ctx->h_active, sizeof(int)));
+    CU(MB.vec.ensure((size_t)10 * vs * 8));
+    CU(MB.basis.ensure((size_t)(restart + 1) * vs * 8));
+    CU(MB.part.ensure((size_t)slices * 2 * rows * 8));
+    CU(MB.blocks.ensure((size_t)nb * kTile * kTile * 8));
+    CU(MB.minv.ensure((size_t)nb * kTile * kTile * 8));
+    CU(MB.sgn.ensure(vec));
+    CU(MB.hflag.ensure(NP));
+    double* v0 = MB.vec.as<double>();
+    double *rhs = v0, *evec = v0 + vs, *wP = v0 + 2 * vs, *shift = v0 + 3 * vs, *sol = v0 + 4 * vs, *gr = v0 + 5 * vs,
+           *gz = v0 + 6 * vs, *gw = v0 + 7 * vs, *tmp = v0 + 8 * vs, *kv = v0 + 9 * vs;
+    (void)kv;
+    CU(cudaMemsetAsync(MB.vec.p, 0, (size_t)10 * vs * 8, st));
+    CU(cudaMemsetAsync(ctx->kr_sc.p, 0, sizeof(KrylovScalars), st));
+    CU(cudaMemsetAsync(ctx->q.p, 0, vec, st));
+    KrylovScalars* sc = (KrylovScalars*)ctx->kr_sc.p;
+
+    // inputs -> device, internal order
+    CU(cudaEventRecord(ctx->ev[0], st));
+    CU(ctx->in_xyz.ensure((size_t)n * 24));
+    CU(ctx->in_chi.ensure(n * 8));
+    CU(ctx->in_hard.ensure(n * 8));
+    CU(cudaMemcpyAsync(ctx->in_xyz.p, io.xyz, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->in_chi.p, io.chi, n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->in_hard.p, io.hard, n * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->perm.p, L.perm.data(), (size_t)NP * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->type.p, L.type.data(), NP, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(MB.hflag.p, hflag.data(), NP, cudaMemcpyHostToDevice, st));
+    if (m > 0) {
+        CU(ctx->pc_type.ensure(m * sizeof(int)));
+        CU(ctx->pc_xyz.ensure(m * 24));
+        CU(ctx->pc_q.ensure(m * 8));
+        CU(cudaMemcpyAsync(ctx->pc_type.p, pc_type.data(), m * sizeof(int), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->pc_xyz.p, io.ext->xyz, m * 24, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->pc_q.p, io.ext->charge, m * 8, cudaMemcpyHostToDevice, st));
+    }
+    CU(cudaStreamSynchronize(st));   // the copies above read pageable host vectors of this scope
+    CU(cudaEventRecord(ctx->ev[1], st));
+    ctx->stats.ms_host_prepare += ms_since(t_host);
+    GatherArgs ga{};
+    ga.NP = NP;
+    ga.n = n;
+    ga.pos_stride = NP;
+    ga.perm = ctx->perm.as<int>();
+    ga.xyz_in = ctx->in_xyz.as<double>();
+    ga.chi_in = ctx->in_chi.as<double>();
+    ga.hard_in = ctx->in_hard.as<double>();
+    ga.x = ctx->x.as<double>();
+    ga.y = ctx->y.as<double>();
+    ga.z = ctx->z.as<double>();
+    ga.diag = ctx->diag.as<double>();
+    ga.chi = ctx->chi.as<double>();
+    ga.hard = ctx->hard.as<double>();
+    LAUNCH(launch_gather(ga, 1, st));
+    const double* d_vext = nullptr;
+    if (has_ext) {
+        CU(ctx->vext.ensure(vec));
+        VextArgs va{};
+        va.x = ga.x;
+        va.y = ga.y;
+        va.z = ga.z;
+        va.type = ctx->type.as<uint8_t>();
+        va.NP = NP;
+        va.m = m;
+        va.pc_xyz = ctx->pc_xyz.as<double>();
+        va.pc_charge = ctx->pc_q.as<double>();
+        va.pc_type = ctx->pc_type.as<int>();
+        va.field[0] = io.ext->field[0];
+        va.field[1] = io.ext->field[1];
+        va.field[2] = io.ext->field[2];
+        va.v_out = ctx->vext.as<double>();
+        LAUNCH(launch_vext(va, view, ctx->blob.as<char>(), blob_bytes, st));
+        d_vext = ctx->vext.as<double>();
+    }
+    LAUNCH(launch_matfree_rhs(ga.chi, d_vext, ctx->type.as<uint8_t>(), NP, io.total_charge, rhs, evec, st));
+
+    // block-Jacobi preconditioner: factor the 128 x 128 diagonal blocks of A(q = 0)
+    MatfreeArgs ma{};
+    ma.x = ga.x;
+    ma.y = ga.y;
+    ma.z = ga.z;
+    ma.type = ctx->type.as<uint8_t>();
+    ma.diag = ga.diag;
+    ma.shift = shift;
+    ma.NP = NP;
+    ma.row0 = row0;
+    ma.rows = rows;
+    ma.slices = slices;
+    ma.vstride = vs;
+    ma.part = MB.part.as<double>();
+    ma.rcut2_max = rcut2_max;
+    LAUNCH(launch_assemble_diag_blocks(ma, view, ctx->blob.as<char>(), blob_bytes, MB.blocks.as<double>(), st));
+    LAUNCH(launch_potrf_tile(MB.blocks.as<double>(), kTile, (long)kTile * kTile, MB.minv.as<double>(), (long)kTile * kTile,
+                             MB.sgn.as<double>(), kTile, nullptr, nullptr, 0, nullptr, kPivotTol, nb, st));
+    auto apply_P = [&](const double* in, double* out) -> int {
+        LAUNCH(launch_block_jacobi_apply(MB.minv.as<double>(), MB.sgn.as<double>(), in, tmp, NP, 1, vs, st));
+        LAUNCH(launch_precond_border(tmp, in, evec, wP, sc, out, NP, st));
+        return CHEQ_OK;
+    };
+    LAUNCH(launch_block_jacobi_apply(MB.minv.as<double>(), MB.sgn.as<double>(), evec, wP, NP, 1, vs, st));
+    LAUNCH(launch_precond_den(evec, wP, sc, NP, st));   // sc->g = 0: den = e . P_A^-1 e
+    uint64_t matvecs = 0;
+    auto apply_K = [&](const double* v, double* out) -> int {
+        MatfreeArgs a = ma;
+        a.vin = v;
+        a.out = out;
+        LAUNCH(launch_matfree_matvec(a, 1, view, ctx->blob.as<char>(), blob_bytes, st));
+        if (world > 1)
+            NC(g_nccl.AllGather(out + row0, out, (size_t)rows, kNcclDouble, ctx->comm, st));
+        LAUNCH(launch_matfree_border(a, 1, st));
+        ++matvecs;
+        return CHEQ_OK;
+    };
+    CU(cudaEventRecord(ctx->ev[2], st));
+    CU(cudaEventRecord(ctx->ev[3], st));
+
+    GmresWork G;
+    G.len = NP + 1;
+    G.vs = vs;
+    G.m = restart;
+    G.max_steps = ctx->matfree_max_steps;
+    G.r = gr;
+    G.z = gz;
+    G.w = gw;
+    G.V = MB.basis.as<double>();
+    G.sc = sc;
+    G.stall_accept = 1e2;
+    const double tol = ctx->matfree_tol;
+
+    ScfState* state = ctx->state.as<ScfState>();
+    double damping0 = 1.0;
+    if (L.scf && o.damping_kind != CHEQ_DAMPING_NONE) damping0 = o.damping_value;
+    LAUNCH(launch_scf_init(state, damping0, 1, st));
+    double* q = ctx->q.as<double>();
+    double* xs = ctx->xsol.as<double>();
+    const uint32_t max_it = L.scf ? o.max_iterations : 1;
+    int status = CHEQ_OK;
+    for (uint32_t it = 1; it <= max_it; ++it) {
+        if (L.scf) LAUNCH(launch_matfree_shift(ga.hard, q, MB.hflag.as<uint8_t>(), NP, shift, st));
+        int steps = 0;
+        bool ok = false;
+        rc = gmres_solve(ctx, G, apply_K, apply_P, rhs, sol, tol, &steps, &ok);
+        if (rc) return rc;
+        if (!ok) {
+            status = CHEQ_ERR_LINALG;
+            ctx->err = "matrix-free GMRES did not converge in " + std::to_string(steps) + " operator applications";
+            break;
+        }
+        LAUNCH(launch_matfree_unpack(sol, NP, xs, state, st));
+        LAUNCH(launch_scf_mix(xs, q, NP, ctx->type.as<uint8_t>(), NP, state, 1, st));
+        CU(cudaMemsetAsync(ctx->active.p, 0, sizeof(int), st));
+        LAUNCH(launch_scf_decide(state, L.scf ? o.tolerance : INFINITY, L.scf ? o.damping_kind : CHEQ_DAMPING_NONE, 1,
+                                 ctx->active.as<int>(), st));
+        CU(cudaMemcpyAsync(ctx->h_active, ctx->active.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ctx->h_state, ctx->state.p, sizeof(ScfState), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        ctx->trace.push_back({ctx->h_state[0].delta, 2, steps});
+        if (*ctx->h_active == 0) break;
+    }
+    CU(cudaMemcpyAsync(ctx->h_state, ctx->state.p, sizeof(ScfState), cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(ctx->ev[4], st));
+    CU(cudaStreamSynchronize(st));
+    ctx->stats.matfree_matvecs = matvecs;
+    ctx->stats.matfree_pairs = (double)matvecs * (double)n * (double)(n - 1);
+    if (status != CHEQ_OK) return status;
+
+    Prepared P;
+    P.L = L;
+    int worst = CHEQ_OK;
+    rc = emit_results(ctx, io, P, 0, 1, &worst);
+    if (rc) return rc;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    ctx->stats.ms_h2d += ms;
+    cudaEventElapsedTime(&ms, ctx->ev[1], ctx->ev[2]);
+    ctx->stats.ms_assemble += ms;
+    cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]);
+    ctx->stats.ms_scf += ms;
+    return worst;
+}
+
 int solve_impl(cheq_ctx* ctx, const SolveIO& io) {
     std::lock_guard<std::mutex> lock(ctx->mu);
     LocalCallGuard local_guard(ctx, io.collective && io.frames == 1);
@@ -2134,7 +2442,15 @@ int solve_impl(cheq_ctx* ctx, const SolveIO& io) {
         CU(cudaMemGetInfo(&free_b, &total_b));
         const double np = (double)io.n + 2.0 * kTile;
         const double need = 8.0 * np * (np + kRhsRows);
-        if (need > (double)total_b)
+        const bool too_big = need > 0.97 * (double)total_b;
+        if (io.frames == 1 && !io.device_ptrs && (io.path == 2 || (io.path == 0 && too_big))) {
+            // matrix-free path: chosen explicitly (cheq_solve_iterative) or because the matrix does not fit
+            const int rcm = solve_matfree(ctx, io);
+            ctx->stats.kernel_launches = ctx->launches;
+            ctx->stats.ms_total = ms_since(t_total);
+            return rcm;
+        }
+        if (too_big)
             return fail(ctx, CHEQ_ERR_OUT_OF_MEMORY,
                         "dense direct solve of " + std::to_string(io.n) + " atoms needs at least " +
                             std::to_string((size_t)(need / 1073741824.0)) + " GiB for the matrix; the device has " +
@@ -2287,6 +2603,9 @@ int32_t cheq_ctx_create(int32_t device, cheq_ctx** out) {
         return CHEQ_ERR_CUDA;
     }
     if (const char* env = getenv("CHEQ_MORTON")) ctx->morton = atoi(env) != 0;
+    if (const char* env = getenv("CHEQ_MATFREE_RESTART")) ctx->matfree_restart = atoi(env);
+    if (const char* env = getenv("CHEQ_MATFREE_MAX_STEPS")) ctx->matfree_max_steps = std::max(10, atoi(env));
+    if (const char* env = getenv("CHEQ_MATFREE_TOL")) ctx->matfree_tol = atof(env);
     if (const char* env = getenv("CHEQ_KRYLOV")) ctx->krylov_mode = atoi(env) != 0;
     if (const char* env = getenv("CHEQ_KRYLOV_MIN_NH")) ctx->krylov_min_nhp = std::max(128, atoi(env));
     if (const char* env = getenv("CHEQ_KRYLOV_FREEZE_EV")) ctx->krylov_freeze_ev = atof(env);
@@ -2332,6 +2651,11 @@ void cheq_ctx_destroy(cheq_ctx* ctx) {
                             &ctx->state, &ctx->active, &ctx->blob, &ctx->pc_xyz, &ctx->pc_q, &ctx->pc_type,
                             &ctx->out_q, &ctx->misc0, &ctx->misc1, &ctx->misc2, &ctx->lu_f, &ctx->lu_piv, &ctx->sgn, &ctx->sgn_flags, &ctx->xsol};
     for (DeviceBuffer* b : bufs) b->release();
+    if (ctx->mf) {
+        ctx->mf->release();
+        delete ctx->mf;
+        ctx->mf = nullptr;
+    }
     ctx->kr_R.release();
     ctx->kr_part.release();
     ctx->kr_vec.release();
@@ -2479,6 +2803,30 @@ int32_t cheq_solve(cheq_ctx* ctx, uint64_t n_atoms, const double* xyz, const dou
     io.iterations_out = iterations_out;
     io.delta_out = delta_out;
     io.collective = true;
+    return solve_impl(ctx, io);
+}
+
+int32_t cheq_solve_iterative(cheq_ctx* ctx, uint64_t n_atoms, const double* xyz, const double* chi,
+                             const double* hardness, const double* radius, const uint8_t* n_quantum, double total_charge,
+                             const cheq_options* options, const cheq_external* external, double* charges_out,
+                             double* potential_out, uint32_t* iterations_out, double* delta_out) {
+    if (!ctx) return CHEQ_ERR_INVALID_ARGUMENT;
+    SolveIO io;
+    io.n = (long)n_atoms;
+    io.xyz = xyz;
+    io.chi = chi;
+    io.hard = hardness;
+    io.radius = radius;
+    io.nq = n_quantum;
+    io.total_charge = total_charge;
+    io.opt = options;
+    io.ext = external;
+    io.charges_out = charges_out;
+    io.potential_out = potential_out;
+    io.iterations_out = iterations_out;
+    io.delta_out = delta_out;
+    io.collective = true;
+    io.path = 2;
     return solve_impl(ctx, io);
 }
 

@@ -176,13 +176,14 @@ cudaError_t launch_scf_init(ScfState* state, double damping, int batch, cudaStre
 
 // ---- stale-factor SCF iterations (kernels_krylov.cu) ------------------------------------------------------------
 // Device-resident scalars of the reduced bordered hydrogen system (see kernels_krylov.cu)
+constexpr int kGmresMaxBasis = 256;   // largest restart length of the GMRES driver (engine.cu)
 struct KrylovScalars {
     double g, h;                    // 1_x^T A_xx^-1 1_x,  1_x^T A_xx^-1 c_x
     double den;                     // t1 . (S_s^-1 t1) + g of the frozen factor
     unsigned long long dmax_bits;   // running max |d_new - d_ref| (positive doubles compare as integers)
-    double dots[72];                // Gram-Schmidt coefficients of the current step, then w . w
-    double hsum[72];                // accumulated coefficients of both Gram-Schmidt passes
-    double y[72];                   // least-squares solution uploaded by the host
+    double dots[kGmresMaxBasis + 8];   // Gram-Schmidt coefficients of the current step; [kGmresMaxBasis + 1]: w . w
+    double hsum[kGmresMaxBasis + 8];   // accumulated coefficients of both Gram-Schmidt passes
+    double y[kGmresMaxBasis + 8];      // least-squares solution uploaded by the host
 };
 
 struct TileMatvecArgs {
@@ -235,6 +236,12 @@ cudaError_t launch_krylov_finish(const double* A, long lda, int NP, int nxp, con
                                  double* x, ScfState* state, cudaStream_t stream);
 cudaError_t launch_krylov_capture(const double* x, int nxp, int nhp, const ScfState* state, double* sol,
                                   cudaStream_t stream);
+
+cudaError_t launch_matfree_rhs(const double* chi, const double* vext, const uint8_t* type, int NP, double total_charge,
+                               double* rhs, double* e, cudaStream_t stream);
+cudaError_t launch_matfree_shift(const double* hard, const double* q, const uint8_t* hflag, int NP, double* d,
+                                 cudaStream_t stream);
+cudaError_t launch_matfree_unpack(const double* sol, int NP, double* x, ScfState* state, cudaStream_t stream);
 
 // ---- LU fallback (kernels_lu.cu) ------------------------------------------------------------------------------
 int lu_padded_size(int NP);

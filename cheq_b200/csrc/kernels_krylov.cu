@@ -192,7 +192,8 @@ gs_update_kernel(const double* V, long stride, double* w, int len, const double*
         for (int k = 0; k < m; ++k) s = fma(-h[k], V[(long)k * stride + i], s);
         w[i] = s;
     }
-    if (blockIdx.x == 0 && threadIdx.x < m) hsum[threadIdx.x] = first ? h[threadIdx.x] : hsum[threadIdx.x] + h[threadIdx.x];
+    if (blockIdx.x == 0)
+        for (int k = threadIdx.x; k < m; k += 256) hsum[k] = first ? h[k] : hsum[k] + h[k];
 }
 
 // dst = src / sqrt(*norm2)
@@ -353,7 +354,57 @@ krylov_capture_kernel(const double* x, int nxp, int nhp, const ScfState* state, 
     if (i == nhp) sol[nhp] = state->mu;
 }
 
+// matrix-free path: rhs = [-(chi + v_ext); Q], e = indicator of the real atoms (0 on padding and in the border slot)
+__global__ void __launch_bounds__(256)
+matfree_rhs_kernel(const double* chi, const double* vext, const uint8_t* type, int NP, double total_charge, double* rhs,
+                   double* e) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < NP) {
+        const bool real = type[i] != kPadType;
+        rhs[i] = real ? -(chi[i] + (vext ? vext[i] : 0.0)) : 0.0;
+        e[i] = real ? 1.0 : 0.0;
+    } else if (i == NP) {
+        rhs[NP] = total_charge;
+        e[NP] = 0.0;
+    }
+}
+
+// matrix-free path: d_i = hardness_i f clamp(q_i, +-0.95) on the n == 1 atoms (implementation.rs:567-572), else 0
+__global__ void __launch_bounds__(256)
+matfree_shift_kernel(const double* hard, const double* q, const uint8_t* hflag, int NP, double* d) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= NP) return;
+    double v = 0.0;
+    if (hflag[i]) v = hard[i] * (fmin(fmax(q[i], -0.95), 0.95) * kHChargeFactor);
+    d[i] = v;
+}
+
+// x[0..NP) and mu from the bordered solution vector
+__global__ void __launch_bounds__(256)
+matfree_unpack_kernel(const double* sol, int NP, double* x, ScfState* state) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < NP) x[i] = sol[i];
+    if (i == 0) state->mu = sol[NP];
+}
+
 }  // namespace
+
+cudaError_t launch_matfree_rhs(const double* chi, const double* vext, const uint8_t* type, int NP, double total_charge,
+                               double* rhs, double* e, cudaStream_t stream) {
+    matfree_rhs_kernel<<<(NP + 256) / 256, 256, 0, stream>>>(chi, vext, type, NP, total_charge, rhs, e);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_matfree_shift(const double* hard, const double* q, const uint8_t* hflag, int NP, double* d,
+                                 cudaStream_t stream) {
+    matfree_shift_kernel<<<(NP + 255) / 256, 256, 0, stream>>>(hard, q, hflag, NP, d);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_matfree_unpack(const double* sol, int NP, double* x, ScfState* state, cudaStream_t stream) {
+    matfree_unpack_kernel<<<(NP + 255) / 256, 256, 0, stream>>>(sol, NP, x, state);
+    return cudaGetLastError();
+}
 
 // ---------------------------------------------------------------------------------------------------------------
 cudaError_t launch_tile_matvec(const TileMatvecArgs& a, bool do_n, bool do_t, cudaStream_t stream) {

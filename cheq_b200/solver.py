@@ -191,8 +191,10 @@ class QEqSolver:
         del keep
         return res
 
-    def solve_arrays(self, xyz, chi, hard, rad, nq, total_charge, ext_struct=None) -> CalculationResult:
-        """One FFI call on already-resolved per-atom arrays (host numpy)."""
+    def solve_arrays(self, xyz, chi, hard, rad, nq, total_charge, ext_struct=None,
+                     iterative: bool = False) -> CalculationResult:
+        """One FFI call on already-resolved per-atom arrays (host numpy).  iterative=True forces the matrix-free
+        path (cheq_solve_iterative); cheq_solve picks it by itself when the dense matrix cannot fit the device."""
         ctx = self.context
         n = len(chi)
         opt = make_options(self.options)
@@ -200,7 +202,8 @@ class QEqSolver:
         pot = C.c_double()
         its = C.c_uint32()
         delta = C.c_double()
-        rc = ctx._lib.cheq_solve(ctx.handle, n, _ptr(xyz), _ptr(chi), _ptr(hard), _ptr(rad), _ptr(nq),
+        fn = ctx._lib.cheq_solve_iterative if iterative else ctx._lib.cheq_solve
+        rc = fn(ctx.handle, n, _ptr(xyz), _ptr(chi), _ptr(hard), _ptr(rad), _ptr(nq),
                                  float(total_charge), C.byref(opt),
                                  C.byref(ext_struct) if ext_struct is not None else None, _ptr(charges),
                                  C.byref(pot), C.byref(its), C.byref(delta))

@@ -96,6 +96,9 @@ typedef struct cheq_stats {
     uint64_t krylov_steps;
     double krylov_ms;        /* device time of those iterations (CUDA events), incl. building R = L^-T S */
     double krylov_bytes;     /* algorithmic bytes streamed by the tiled matrix-vector kernels in them */
+    /* matrix-free path (cheq_solve_iterative): operator applications and the pair integrals they recomputed */
+    uint64_t matfree_matvecs;
+    double matfree_pairs;
 } cheq_stats;
 
 int32_t cheq_ctx_create(int32_t device, cheq_ctx** out);
@@ -156,6 +159,21 @@ int32_t cheq_solve(cheq_ctx* ctx, uint64_t n_atoms, const double* xyz, const dou
                    double total_charge, const cheq_options* options, const cheq_external* external,
                    double* charges_out, double* potential_out, uint32_t* iterations_out,
                    double* delta_out);
+
+/*
+ * The same solve WITHOUT ever forming the (N + 1)^2 matrix (the reference keeps three copies of it,
+ * implementation.rs:464, 282, 575): restarted GMRES on the bordered system in every SCF iteration, the shielded-
+ * Coulomb tiles recomputed on the fly in each operator application, block-Jacobi preconditioner over 128-atom
+ * clusters.  Memory O(N) per GPU; on a joined context the rows of the operator are sharded over the ranks (one
+ * ncclAllGather per application).  cheq_solve switches to this path by itself when the dense matrix cannot fit the
+ * device; this entry point forces it (parity tests, large-N runs).  Same arguments, outputs and status codes as
+ * cheq_solve; CHEQ_ERR_LINALG if GMRES does not reach its tolerance.
+ */
+int32_t cheq_solve_iterative(cheq_ctx* ctx, uint64_t n_atoms, const double* xyz, const double* chi,
+                             const double* hardness, const double* radius, const uint8_t* n_quantum,
+                             double total_charge, const cheq_options* options, const cheq_external* external,
+                             double* charges_out, double* potential_out, uint32_t* iterations_out,
+                             double* delta_out);
 
 /* Same, with xyz/chi/hardness/radius/n_quantum/charges_out (and the external arrays) in DEVICE memory. */
 int32_t cheq_solve_device(cheq_ctx* ctx, uint64_t n_atoms, const double* d_xyz, const double* d_chi,

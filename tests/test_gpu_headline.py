@@ -169,3 +169,63 @@ def test_pair_integrals_ulp_bound(gpu_ctx, oracle):
         sel = slice(0, 2000) if basis == 1 else slice(0, n)     # STO: the far pairs (F = 0), where only 1/R matters
         ulps = np.abs(out[sel] - ref[sel]) / np.spacing(np.abs(ref[sel]))
         assert ulps.max() <= (8.0 if basis == 1 else 16.0), (basis, ulps.max())
+
+
+# ---- matrix-free path (SURVEY section 8(e) last row) -----------------------------------------------------------
+def _external_struct(ext):
+    import ctypes as C
+    from cheq_b200 import _ffi
+    _, _, prad, pnq = workloads.gather_parameters(ext["Z"], get_default_parameters())
+    e = _ffi.External()
+    pxyz, pq = np.ascontiguousarray(ext["xyz"]), np.ascontiguousarray(ext["q"])
+    e.num_point_charges = len(pq)
+    e.xyz, e.charge = pxyz.ctypes.data_as(C.c_void_p), pq.ctypes.data_as(C.c_void_p)
+    e.radius, e.n = prad.ctypes.data_as(C.c_void_p), pnq.ctypes.data_as(C.c_void_p)
+    e.field[0], e.field[1], e.field[2] = ext["field"]
+    return e, (pxyz, pq, prad, pnq)
+
+
+def test_matrix_free_path_parity_vs_oracle(gpu_ctx, oracle):
+    """cheq_solve_iterative (GMRES, J tiles recomputed on the fly, block-Jacobi over 128-atom clusters) against the
+    CPU oracle: same SCF trajectory, charges to 1e-8 e, potential to 1e-8 eV -- vacuum, GTO, no SCF, field + charges."""
+    from cheq_b200 import BasisType
+    P = get_default_parameters()
+    cases = []
+    Z, xyz = workloads.water_cluster(250)
+    cases += [("water750/STO", Z, xyz, {}, None), ("water750/GTO", Z, xyz, {"basis_type": BasisType.Gto}, None),
+              ("water750/no-scf", Z, xyz, {"hydrogen_scf": False}, None)]
+    Zo, xo = workloads.organic_chain(1000)
+    cases.append(("organic1000", Zo, xo, {}, None))
+    Z3, x3, ext = workloads.water_box_3k()
+    cases.append(("B3k field+charges", Z3, x3, {}, ext))
+    for name, Zc, xc, kw, ex in cases:
+        o = SolverOptions(**kw)
+        chi, hard, rad, nq = workloads.gather_parameters(Zc, P)
+        es, keep = _external_struct(ex) if ex else (None, None)
+        s = QEqSolver(P, o, gpu_ctx)
+        res = s.solve_arrays(np.ascontiguousarray(xc), chi, hard, rad, nq, 0.0, es, iterative=True)
+        trace, st = gpu_ctx.scf_trace(), gpu_ctx.stats()
+        from test_gpu_parity import oracle_opts
+        ref = oracle.solve(Zc, xc, 0.0, oracle_opts(oracle, o), external=ex)
+        assert st["matfree_matvecs"] > 0 and all(t[1] == 2 for t in trace)
+        print(f"[{name}] matvecs {st['matfree_matvecs']}  GMRES steps per SCF iteration {[t[2] for t in trace]}")
+        assert_trajectory(res, trace, ref, f"matrix-free {name}")
+
+
+def test_matrix_free_vs_dense_w8k(gpu_ctx):
+    """8,100 atoms: the matrix-free path against the dense direct path of the same engine."""
+    Z, xyz = workloads.water_cluster(2700)
+    chi, hard, rad, nq = workloads.gather_parameters(Z, get_default_parameters())
+    s = QEqSolver(get_default_parameters(), SolverOptions(), gpu_ctx)
+    x = np.ascontiguousarray(xyz)
+    dense = s.solve_arrays(x, chi, hard, rad, nq, 0.0)
+    t0 = time.perf_counter()
+    it = s.solve_arrays(x, chi, hard, rad, nq, 0.0, iterative=True)
+    dt = time.perf_counter() - t0
+    st = gpu_ctx.stats()
+    dq = float(np.max(np.abs(np.array(it.charges) - np.array(dense.charges))))
+    print(f"[W8k matrix-free vs dense] iterations {it.iterations}/{dense.iterations} dq {dq:.2e} "
+          f"dmu {abs(it.equilibrated_potential - dense.equilibrated_potential):.2e}  {st['matfree_matvecs']} matvecs, "
+          f"{st['matfree_pairs'] / dt / 1e9:.1f} G pairs/s incl. everything, {dt:.2f} s")
+    assert it.iterations == dense.iterations and dq <= Q_TOL
+    assert abs(it.equilibrated_potential - dense.equilibrated_potential) <= MU_TOL
