@@ -1265,20 +1265,47 @@ struct Krylov {
     bool ready = false;                         // buffers allocated, per-geometry scalars set
     bool frozen = false;                        // R, ws, den describe the factor currently in the trapezoid
     double bytes = 0.0;
+    // group of GPUs: S0 is held by tile columns (col_mask: the columns this rank owns), R by a contiguous chunk of
+    // tile rows [ra, rb) sized for equal work in its construction; partial products are summed with ncclAllReduce
+    bool dist = false;
+    const uint8_t* col_mask = nullptr;
+    int ra = 0, rb = 0;
 };
 
-int krylov_alloc(cheq_ctx* ctx, Krylov& K, int nhp) {
+// sums the (n + 1)-vector over the ranks of the group (identical result on every rank)
+int krylov_allreduce(cheq_ctx* ctx, const Krylov& K, double* v) {
+    if (!K.dist) return CHEQ_OK;
+    NC(g_nccl.AllReduce(v, v, (size_t)K.len, kNcclDouble, 0 /* ncclSum */, ctx->comm, ctx->stream));
+    return CHEQ_OK;
+}
+
+int krylov_alloc(cheq_ctx* ctx, Krylov& K, int nhp, bool dist) {
     K.nhp = nhp;
     K.nt = nhp / kTile;
     K.len = nhp + 1;
     K.vs = nhp + 8;
-    CU(ctx->kr_R.ensure((size_t)nhp * nhp * 8));
+    K.dist = dist;
+    K.ra = 0;
+    K.rb = K.nt;
+    if (dist) {
+        // row tile i of R costs ~ (nt - i)^2 in the construction: chunk boundaries at equal cumulative cost
+        auto bound = [&](int k) {
+            const double f = 1.0 - std::cbrt(1.0 - (double)k / ctx->world);
+            return std::min(K.nt, std::max(0, (int)std::lround(K.nt * f)));
+        };
+        K.ra = bound(ctx->rank);
+        K.rb = (ctx->rank == ctx->world - 1) ? K.nt : bound(ctx->rank + 1);
+        if (K.rb <= K.ra) K.ra = K.rb = K.nt + 1;   // no rows here: a range that matches no tile (0, 0 would mean "all")
+    }
+    const size_t r_rows = (size_t)std::max(1, K.rb - K.ra) * kTile;
+    CU(ctx->kr_R.ensure(r_rows * nhp * 8));
     CU(ctx->kr_part.ensure((size_t)2 * K.nt * K.nt * kTile * 8));
     const size_t nvec = 12 + Krylov::kMaxBasis + 1;
     CU(ctx->kr_vec.ensure(nvec * K.vs * 8));
     CU(ctx->kr_sc.ensure(sizeof(KrylovScalars)));
     if (!ctx->h_ksc) CU(cudaMallocHost((void**)&ctx->h_ksc, sizeof(KrylovScalars)));
-    K.R = ctx->kr_R.as<double>();
+    // R is addressed with GLOBAL tile-row indices: the base is shifted up by the rows this rank does not hold
+    K.R = ctx->kr_R.as<double>() - (long)K.ra * kTile;
     K.partN = ctx->kr_part.as<double>();
     K.partT = K.partN + (size_t)K.nt * K.nt * kTile;
     double* v = ctx->kr_vec.as<double>();
@@ -1299,20 +1326,28 @@ int krylov_apply_sinv(cheq_ctx* ctx, Krylov& K, const double* in, double* out) {
     cudaStream_t st = ctx->stream;
     TileMatvecArgs a{};
     a.M = K.R;
-    a.ld = K.nhp;
+    a.ld = (long)(K.rb - K.ra) * kTile;
     a.nt = K.nt;
     a.upper = 1;
     a.xT = in;
     a.partN = K.partN;
     a.partT = K.partT;
+    a.row_begin = K.ra;
+    a.row_end = K.rb;
     LAUNCH(launch_tile_matvec(a, false, true, st));
     TileReduceArgs r{};
     r.nt = K.nt;
     r.upper = 1;
     r.op = 0;
+    r.row_begin = K.ra;
+    r.row_end = K.rb;
     r.partT = K.partT;
     r.out = K.tmp1;
     LAUNCH(launch_tile_matvec_reduce(r, st));
+    if (K.dist) {
+        CU(cudaMemsetAsync(K.tmp1 + K.nhp, 0, sizeof(double), st));
+        if (int rc = krylov_allreduce(ctx, K, K.tmp1)) return rc;
+    }
     a.xT = nullptr;
     a.xN = K.tmp1;
     a.scaleN = K.sgn_h;
@@ -1321,7 +1356,11 @@ int krylov_apply_sinv(cheq_ctx* ctx, Krylov& K, const double* in, double* out) {
     r.partN = K.partN;
     r.out = out;
     LAUNCH(launch_tile_matvec_reduce(r, st));
-    K.bytes += 8.0 * (double)K.nhp * (K.nhp + 1.0);
+    if (K.dist) {
+        CU(cudaMemsetAsync(out + K.nhp, 0, sizeof(double), st));
+        if (int rc = krylov_allreduce(ctx, K, out)) return rc;
+    }
+    K.bytes += 8.0 * (double)K.nhp * (K.nhp + 1.0) / (K.dist ? ctx->world : 1);
     return CHEQ_OK;
 }
 
@@ -1338,6 +1377,7 @@ int krylov_apply_K(cheq_ctx* ctx, Krylov& K, const double* v, double* out, int o
     a.xT = v;
     a.partN = K.partN;
     a.partT = K.partT;
+    a.col_mask = K.col_mask;
     LAUNCH(launch_tile_matvec(a, true, true, st));
     TileReduceArgs r{};
     r.nt = K.nt;
@@ -1345,6 +1385,8 @@ int krylov_apply_K(cheq_ctx* ctx, Krylov& K, const double* v, double* out, int o
     r.op = op;
     r.partN = K.partN;
     r.partT = K.partT;
+    r.col_mask = K.col_mask;
+    r.border_owner = (!K.dist || ctx->rank == 0) ? 1 : 0;
     r.v = v;
     r.d = K.d_cur;
     r.t1 = K.t1;
@@ -1352,7 +1394,8 @@ int krylov_apply_K(cheq_ctx* ctx, Krylov& K, const double* v, double* out, int o
     r.sc = K.sc;
     r.out = out;
     LAUNCH(launch_tile_matvec_reduce(r, st));
-    K.bytes += 4.0 * (double)K.nhp * (K.nhp + 1.0);
+    if (int rc = krylov_allreduce(ctx, K, out)) return rc;
+    K.bytes += 4.0 * (double)K.nhp * (K.nhp + 1.0) / (K.dist ? ctx->world : 1);
     return CHEQ_OK;
 }
 
@@ -1369,17 +1412,19 @@ int krylov_apply_precond(cheq_ctx* ctx, Krylov& K, const double* in, double* out
 // M^T = (S L_jj^-1)^T; update: C -= A S B^T), restricted to the rows that can be non-zero.  n_h^3 / 3 flops.
 int krylov_build_R(Dense& D, Krylov& K, int h0, int j0, int n) {
     cheq_ctx* ctx = D.ctx;
-    const long ldr = K.nhp;
+    const long ldr = (long)(K.rb - K.ra) * kTile;      // this rank's rows [ra, rb) of R (global row indices, shifted base)
+    const long r0 = (long)K.ra * kTile;
     if (n == kTile) {
+        const int mt = std::min(K.rb, (j0 + kTile) / kTile) - K.ra;
+        if (mt <= 0) return CHEQ_OK;
         GemmArgs g{};
-        g.A = K.R + (long)j0 * ldr;
+        g.A = K.R + r0 + (long)j0 * ldr;
         g.lda = ldr;
         g.B = D.Linv + (long)((h0 + j0) / kTile) * kTile * kTile;
         g.ldb = kTile;
-        g.C = K.R + (long)j0 * ldr;
+        g.C = K.R + r0 + (long)j0 * ldr;
         g.ldc = ldr;
         g.K = kTile;
-        const int mt = (j0 + kTile) / kTile;
         const double fl = 2.0 * mt * (double)kTile * kTile * kTile;
         D.flops += fl;
         return launch_gemm_timed(ctx, g, mt, 1, 1, fl);
@@ -1387,23 +1432,24 @@ int krylov_build_R(Dense& D, Krylov& K, int h0, int j0, int n) {
     const int n1 = ((n / kTile) / 2) * kTile;
     int rc = krylov_build_R(D, K, h0, j0, n1);
     if (rc) return rc;
-    {
+    const int mt_u = std::min(K.rb, (j0 + n1) / kTile) - K.ra;
+    if (mt_u > 0) {
         GemmArgs g{};
-        g.A = K.R + (long)j0 * ldr;
+        g.A = K.R + r0 + (long)j0 * ldr;
         g.lda = ldr;
         g.B = D.A + (long)(h0 + j0 + n1) + (long)(h0 + j0) * D.ld;
         g.ldb = D.ld;
-        g.C = K.R + (long)(j0 + n1) * ldr;
+        g.C = K.R + r0 + (long)(j0 + n1) * ldr;
         g.ldc = ldr;
         g.K = n1;
         g.subtract = 1;
         g.neg_cnt = D.neg_cnt + (h0 + j0) / kTile;
         g.neg_idx = D.neg_idx + (long)(h0 + j0);
         g.strideNeg = D.strideNeg;
-        const int mt = (j0 + n1) / kTile, nt = (n - n1) / kTile;
-        const double fl = 2.0 * (double)(j0 + n1) * (double)(n - n1) * (double)n1;
+        const int nt = (n - n1) / kTile;
+        const double fl = 2.0 * (double)mt_u * kTile * (double)(n - n1) * (double)n1;
         D.flops += fl;
-        rc = launch_gemm_timed(ctx, g, mt, nt, 1, fl);
+        rc = launch_gemm_timed(ctx, g, mt_u, nt, 1, fl);
         if (rc) return rc;
     }
     return krylov_build_R(D, K, h0, j0 + n1, n - n1);
@@ -1412,7 +1458,7 @@ int krylov_build_R(Dense& D, Krylov& K, int h0, int j0, int n) {
 // Freeze the factor that is in the trapezoid (it belongs to the diagonal shift `d_of_factor`).
 int krylov_freeze(cheq_ctx* ctx, Dense& D, Krylov& K, int nxp, const double* d_of_factor) {
     cudaStream_t st = ctx->stream;
-    LAUNCH(launch_set_identity_tiles(K.R, K.nhp, K.nt, st));
+    LAUNCH(launch_set_identity_tiles(K.R + (long)K.ra * kTile, (long)(K.rb - K.ra) * kTile, K.nt, K.ra, K.rb, st));
     int rc = krylov_build_R(D, K, nxp, 0, K.nhp);
     if (rc) return rc;
     CU(cudaMemcpyAsync(K.d_frozen, d_of_factor, (size_t)K.nhp * 8, cudaMemcpyDeviceToDevice, st));
@@ -1940,20 +1986,41 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
     // Stale-factor iterations (kernels_krylov.cu): one frame, one GPU, a hydrogen block that is worth it, and room
     // for R (nhp^2 doubles).  Otherwise every iteration refactors the hydrogen block.
     Krylov K;
-    bool kry = batch == 1 && !dist && ctx->krylov_mode && L.nhp >= ctx->krylov_min_nhp;
+    bool kry = batch == 1 && ctx->krylov_mode && L.nhp >= ctx->krylov_min_nhp;
     if (kry) {
+        // room for R (all of it on one GPU, the largest row chunk -- about half -- in a group); every rank of a group
+        // must take the same decision, and they do: same sizes, same device type, same allocations so far
         size_t free_b = 0, total_b = 0;
         CU(cudaMemGetInfo(&free_b, &total_b));
-        const size_t need = (size_t)L.nhp * L.nhp * 8 + ((size_t)64 << 20);
+        const size_t need = (size_t)L.nhp * L.nhp * 8 / (dist ? 2 : 1) + ((size_t)256 << 20);
         if (need > free_b + ctx->kr_R.cap) kry = false;
+        if (dist) {
+            int* flag = ctx->ipc_stage.as<int>() + 32;
+            const int mine = kry ? 1 : 0;
+            CU(cudaMemcpyAsync(flag, &mine, sizeof(int), cudaMemcpyHostToDevice, st));
+            NC(g_nccl.AllReduce(flag, flag, 1, kNcclInt, 3 /* ncclMin */, ctx->comm, st));
+            int all = 0;
+            CU(cudaMemcpyAsync(&all, flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            kry = all != 0;
+        }
     }
     if (kry) {
-        rc = krylov_alloc(ctx, K, L.nhp);
+        rc = krylov_alloc(ctx, K, L.nhp, dist);
         if (rc) return rc;
         K.S0 = ctx->S0.as<double>();
         K.ld0 = ld0;
         K.sgn_h = D.sgn + L.nxp;
-        LAUNCH(launch_krylov_setup(D.A, D.ld, L.NP, L.nxp, D.sgn, K.S0, ld0, L.nhp, io.total_charge, K.sc, K.tc, K.t1, st));
+        K.col_mask = mask_h;
+        LAUNCH(launch_krylov_setup(D.A, D.ld, L.NP, L.nxp, D.sgn, K.S0, ld0, L.nhp, io.total_charge, K.sc, K.tc, K.t1,
+                                   mask_h, (!dist || ctx->rank == 0) ? 1 : 0, st));
+        if (dist) {
+            // the reduced right-hand sides live in the owners' columns: complete them on every rank
+            rc = krylov_allreduce(ctx, K, K.tc);
+            if (rc) return rc;
+            rc = krylov_allreduce(ctx, K, K.t1);
+            if (rc) return rc;
+        }
     }
     cudaEvent_t evk0 = ctx->ev[5], evk1 = ctx->ev[6];
     float krylov_ms = 0.0f;

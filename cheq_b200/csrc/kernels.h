@@ -199,10 +199,13 @@ struct TileMatvecArgs {
     double* partN;     // [nt * nt][128] partial results per tile
     double* partT;
     const uint8_t* col_mask;   // nullable: tile columns owned by this rank
+    int row_begin, row_end;    // tile rows held by this rank (row_end == 0: all)
 };
 
 struct TileReduceArgs {
     int nt, upper, op;
+    int row_begin, row_end;    // as in TileMatvecArgs
+    int border_owner;          // op 1: 1 = this rank contributes the border entry (exactly one rank of a group)
     const double* partN;   // nullable
     const double* partT;   // nullable
     const uint8_t* col_mask;
@@ -226,12 +229,14 @@ cudaError_t launch_combine(const double* V, long stride, double* x, int len, con
 cudaError_t launch_precond_border(const double* u0, const double* rin, const double* t1, const double* ws,
                                   const KrylovScalars* sc, double* out, int n, cudaStream_t stream);
 cudaError_t launch_precond_den(const double* t1, const double* ws, KrylovScalars* sc, int n, cudaStream_t stream);
+// col_mask (nullable): tile columns of the hydrogen block owned by this rank; the entries of t_c, t_1 (and the
+// border entry of t_c) that belong to other ranks are written as 0 so that a sum over the ranks completes them
 cudaError_t launch_krylov_setup(const double* A, long lda, int NP, int nxp, const double* sgn, const double* S0,
                                 long ld0, int nhp, double total_charge, KrylovScalars* sc, double* tc, double* t1,
-                                cudaStream_t stream);
+                                const uint8_t* col_mask, int border_owner, cudaStream_t stream);
 cudaError_t launch_h_shift(const double* hard_h, const double* q_h, const uint8_t* type_h, int nhp, double* d_new,
                            const double* d_ref, KrylovScalars* sc, cudaStream_t stream);
-cudaError_t launch_set_identity_tiles(double* R, long ld, int nt, cudaStream_t stream);
+cudaError_t launch_set_identity_tiles(double* R, long ld, int nt, int row_begin, int row_end, cudaStream_t stream);
 cudaError_t launch_krylov_finish(const double* A, long lda, int NP, int nxp, const double* sol, int nhp, double* v,
                                  double* x, ScfState* state, cudaStream_t stream);
 cudaError_t launch_krylov_capture(const double* x, int nxp, int nhp, const ScfState* state, double* sol,

@@ -49,6 +49,7 @@ tile_matvec_kernel(TileMatvecArgs a) {
         __syncthreads();
     }
     if (a.upper ? (i > j) : (i >= a.nt)) return;
+    if (a.row_end > 0 && (i < a.row_begin || i >= a.row_end)) return;   // tile row held by another rank
     const bool diag = (i == j);
     const double* T = a.M + (long)i * kTile + (long)j * kTile * a.ld + lane;
     double xt[4] = {0.0, 0.0, 0.0, 0.0};
@@ -128,12 +129,13 @@ tile_matvec_reduce_kernel(TileReduceArgs a) {
         }
         if (r == 0) {
             const double y = red[0] - a.sc->g * a.v[n];
-            a.out[n] = (a.op == 2) ? (a.rhs[n] - y) : y;
+            a.out[n] = a.border_owner ? ((a.op == 2) ? (a.rhs[n] - y) : y) : 0.0;
         }
         return;
     }
+    const int rb = a.row_begin, re = (a.row_end > 0) ? a.row_end : a.nt;
     double s = 0.0;
-    if (a.partN) {
+    if (a.partN && b >= rb && b < re) {
         // N partials of tiles (b, j): lower j <= b, upper j >= b
         const int j0 = a.upper ? b : 0, j1 = a.upper ? a.nt - 1 : b;
         for (int j = j0; j <= j1; ++j) {
@@ -144,7 +146,7 @@ tile_matvec_reduce_kernel(TileReduceArgs a) {
     if (a.partT) {
         // T partials of tiles (i, b): lower i >= b, upper i <= b
         if (!a.col_mask || a.col_mask[b]) {
-            const int i0 = a.upper ? 0 : b, i1 = a.upper ? b : a.nt - 1;
+            const int i0 = max(a.upper ? 0 : b, rb), i1 = min(a.upper ? b : a.nt - 1, re - 1);
             for (int i = i0; i <= i1; ++i) s += a.partT[((long)b * a.nt + i) * kTile + r];
         }
     }
@@ -259,7 +261,8 @@ precond_den_kernel(const double* t1, const double* ws, KrylovScalars* sc, int n)
 // and the contiguous copies t_c, t_1 of the reduced right-hand sides (rows nhp, nhp + 1 of the snapshot), rhs[n] = Q - h.
 __global__ void __launch_bounds__(1024)
 krylov_setup_kernel(const double* A, long lda, int NP, int nxp, const double* sgn, const double* S0, long ld0, int nhp,
-                    double total_charge, KrylovScalars* sc, double* tc, double* t1) {
+                    double total_charge, KrylovScalars* sc, double* tc, double* t1, const uint8_t* col_mask,
+                    int border_owner) {
     __shared__ double r1[32], r2[32];
     const double* fc = A + NP;
     const double* f1 = fc + 1;
@@ -286,12 +289,13 @@ krylov_setup_kernel(const double* A, long lda, int NP, int nxp, const double* sg
         }
         sc->g = g;
         sc->h = h;
-        tc[nhp] = total_charge - h;
+        tc[nhp] = border_owner ? (total_charge - h) : 0.0;
         t1[nhp] = 0.0;
     }
     for (int k = threadIdx.x; k < nhp; k += 1024) {
-        tc[k] = S0[(long)nhp + (long)k * ld0];
-        t1[k] = S0[(long)nhp + 1 + (long)k * ld0];
+        const bool mine = !col_mask || col_mask[k / kTile];
+        tc[k] = mine ? S0[(long)nhp + (long)k * ld0] : 0.0;
+        t1[k] = mine ? S0[(long)nhp + 1 + (long)k * ld0] : 0.0;
     }
 }
 
@@ -316,11 +320,12 @@ h_shift_kernel(const double* hard_h, const double* q_h, const uint8_t* type_h, i
 }
 
 // R = I (n x n, ld n): zero the upper triangle by tiles, ones on the diagonal
+// R points at the first LOCAL tile row (global tile row row_begin); rows [row_begin, row_end) are held here
 __global__ void __launch_bounds__(256)
-set_identity_tiles_kernel(double* R, long ld, int nt) {
-    const int ti = blockIdx.x, tj = blockIdx.y;
-    if (ti > tj) return;   // only tiles on/above the diagonal are ever touched
-    double* d = R + (long)ti * kTile + (long)tj * kTile * ld;
+set_identity_tiles_kernel(double* R, long ld, int nt, int row_begin, int row_end) {
+    const int ti = row_begin + blockIdx.x, tj = blockIdx.y;
+    if (ti >= row_end || ti > tj) return;   // only tiles on/above the diagonal are ever touched
+    double* d = R + (long)(ti - row_begin) * kTile + (long)tj * kTile * ld;
     for (int idx = threadIdx.x; idx < kTile * kTile / 2; idx += 256) {
         const int r2 = idx & 63, c = idx >> 6;
         double2 v = make_double2(0.0, 0.0);
@@ -459,8 +464,9 @@ cudaError_t launch_precond_den(const double* t1, const double* ws, KrylovScalars
 
 cudaError_t launch_krylov_setup(const double* A, long lda, int NP, int nxp, const double* sgn, const double* S0,
                                 long ld0, int nhp, double total_charge, KrylovScalars* sc, double* tc, double* t1,
-                                cudaStream_t stream) {
-    krylov_setup_kernel<<<1, 1024, 0, stream>>>(A, lda, NP, nxp, sgn, S0, ld0, nhp, total_charge, sc, tc, t1);
+                                const uint8_t* col_mask, int border_owner, cudaStream_t stream) {
+    krylov_setup_kernel<<<1, 1024, 0, stream>>>(A, lda, NP, nxp, sgn, S0, ld0, nhp, total_charge, sc, tc, t1, col_mask,
+                                                border_owner);
     return cudaGetLastError();
 }
 
@@ -470,9 +476,10 @@ cudaError_t launch_h_shift(const double* hard_h, const double* q_h, const uint8_
     return cudaGetLastError();
 }
 
-cudaError_t launch_set_identity_tiles(double* R, long ld, int nt, cudaStream_t stream) {
-    dim3 grid(nt, nt);
-    set_identity_tiles_kernel<<<grid, 256, 0, stream>>>(R, ld, nt);
+cudaError_t launch_set_identity_tiles(double* R, long ld, int nt, int row_begin, int row_end, cudaStream_t stream) {
+    if (row_end <= row_begin) return cudaSuccess;
+    dim3 grid(row_end - row_begin, nt);
+    set_identity_tiles_kernel<<<grid, 256, 0, stream>>>(R, ld, nt, row_begin, row_end);
     return cudaGetLastError();
 }
 

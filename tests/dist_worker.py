@@ -118,6 +118,26 @@ def main():
     # a larger system against the single-GPU engine
     Zb, xb = workloads.water_cluster(big)
     run_case(f"water{3 * big}", Zb, xb, SolverOptions(), oracle_check=False)
+    # stale-factor SCF iterations on the group: S0 by tile columns, R by row chunks, three allreduces per GMRES step
+    ctx.set_krylov(True, 128, 4.5, 5)
+    run_case("water750/STO/scf/stale-factor", Z, xyz, SolverOptions(), tpp=2)
+    assert ctx.stats()["krylov_iterations"] > 0
+    run_case("water750/GTO/scf/stale-factor", Z, xyz, SolverOptions(basis_type=BasisType.Gto), tpp=1)
+    run_case(f"water{3 * big}/stale-factor", Zb, xb, SolverOptions(), oracle_check=False)
+    assert ctx.stats()["krylov_iterations"] > 0
+    ctx.set_krylov(True, 4096, 4.5, 5)
+    # matrix-free path on the group: rows of the operator sharded, one all-gather per application
+    chi, hard, rad, nq = workloads.gather_parameters(Z, P)
+    s_it = QEqSolver(P, SolverOptions(), ctx)
+    res = s_it.solve_arrays(np.ascontiguousarray(xyz), chi, hard, rad, nq, 0.0, None, iterative=True)
+    check_same_everywhere(np.array(res.charges), res.equilibrated_potential, res.iterations)
+    if rank == 0:
+        from oracle import oracle as O
+        ref = O.solve(list(Z), np.asarray(xyz), 0.0)
+        dqo = float(np.max(np.abs(np.array(res.charges) - ref.charges)))
+        assert res.iterations == ref.iterations and dqo <= 1e-8, (res.iterations, ref.iterations, dqo)
+        print(f"water750/matrix-free on {world} rank(s): its={res.iterations} vs oracle dq={dqo:.1e}, "
+              f"{ctx.stats()['matfree_matvecs']} operator applications", flush=True)
     dist.barrier()
     if rank == 0:
         print("DIST PARITY PASS", flush=True)
