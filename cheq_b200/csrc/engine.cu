@@ -2287,8 +2287,11 @@ int solve_matfree(cheq_ctx* ctx, const SolveIO& io) {
     const long vs = NP + 8;
     const int nb = NP / kTile;
     const int rows = NP / world, row0 = rank * rows;
-    int slices = 1;
-    while ((rows / kTile) * slices < 4 * 148 && slices < NP / 256) slices *= 2;
+    // column slices per row tile: enough CTAs (~8 waves of 4 resident CTAs per SM) that the last, partial wave does
+    // not matter, but at least 4 column tiles of 256 per slice
+    const int row_ctas = rows / kTile, col_tiles = NP / 256;
+    int slices = std::max(1, std::min((8 * 4 * 148 + row_ctas - 1) / row_ctas, col_tiles / 4));
+    slices = (col_tiles + (col_tiles + slices - 1) / slices - 1) / ((col_tiles + slices - 1) / slices);   // no empty slice
     CU(ctx->perm.ensure((size_t)NP * sizeof(int)));
     CU(ctx->type.ensure(NP));
     const size_t vec = (size_t)NP * 8;

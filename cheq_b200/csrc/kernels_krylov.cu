@@ -111,24 +111,27 @@ tile_matvec_kernel(TileMatvecArgs a) {
 //   op 0: out = sum                                   (triangular passes)
 //   op 1: out = K v      = sum + d v + nu t1 ;  border: t1.v - g nu
 //   op 2: out = rhs - K v                              (residual)
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(512)
 tile_matvec_reduce_kernel(TileReduceArgs a) {
-    const int b = blockIdx.x, r = threadIdx.x;
+    // 128 rows x 4 groups: group g sums the partials with index = g (mod 4), the groups are combined in order
+    const int b = blockIdx.x, r = threadIdx.x & 127, g = threadIdx.x >> 7;
+    __shared__ double red[4][128];
     if (b == a.nt) {
         // border entry: t1 . v - g nu   (v has n = 128 nt entries, nu = v[n])
         if (a.op == 0) return;
-        __shared__ double red[128];
         const int n = a.nt * kTile;
         double s = 0.0;
-        for (int k = r; k < n; k += 128) s = fma(a.t1[k], a.v[k], s);
-        red[r] = s;
+        for (int k = threadIdx.x; k < n; k += 512) s = fma(a.t1[k], a.v[k], s);
+        red[g][r] = s;
+        __syncthreads();
+        if (g == 0) red[0][r] = (red[0][r] + red[1][r]) + (red[2][r] + red[3][r]);
         __syncthreads();
         for (int off = 64; off > 0; off >>= 1) {
-            if (r < off) red[r] += red[r + off];
+            if (threadIdx.x < off) red[0][threadIdx.x] += red[0][threadIdx.x + off];
             __syncthreads();
         }
-        if (r == 0) {
-            const double y = red[0] - a.sc->g * a.v[n];
+        if (threadIdx.x == 0) {
+            const double y = red[0][0] - a.sc->g * a.v[n];
             a.out[n] = a.border_owner ? ((a.op == 2) ? (a.rhs[n] - y) : y) : 0.0;
         }
         return;
@@ -138,7 +141,7 @@ tile_matvec_reduce_kernel(TileReduceArgs a) {
     if (a.partN && b >= rb && b < re) {
         // N partials of tiles (b, j): lower j <= b, upper j >= b
         const int j0 = a.upper ? b : 0, j1 = a.upper ? a.nt - 1 : b;
-        for (int j = j0; j <= j1; ++j) {
+        for (int j = j0 + g; j <= j1; j += 4) {
             if (a.col_mask && !a.col_mask[j]) continue;
             s += a.partN[((long)j * a.nt + b) * kTile + r];
         }
@@ -147,9 +150,13 @@ tile_matvec_reduce_kernel(TileReduceArgs a) {
         // T partials of tiles (i, b): lower i >= b, upper i <= b
         if (!a.col_mask || a.col_mask[b]) {
             const int i0 = max(a.upper ? 0 : b, rb), i1 = min(a.upper ? b : a.nt - 1, re - 1);
-            for (int i = i0; i <= i1; ++i) s += a.partT[((long)b * a.nt + i) * kTile + r];
+            for (int i = i0 + g; i <= i1; i += 4) s += a.partT[((long)b * a.nt + i) * kTile + r];
         }
     }
+    red[g][r] = s;
+    __syncthreads();
+    if (g != 0) return;
+    s = (red[0][r] + red[1][r]) + (red[2][r] + red[3][r]);
     const int k = b * kTile + r;
     if (a.op != 0) {
         const double nu = a.v[a.nt * kTile];
@@ -421,7 +428,7 @@ cudaError_t launch_tile_matvec(const TileMatvecArgs& a, bool do_n, bool do_t, cu
 }
 
 cudaError_t launch_tile_matvec_reduce(const TileReduceArgs& a, cudaStream_t stream) {
-    tile_matvec_reduce_kernel<<<a.nt + (a.op != 0 ? 1 : 0), 128, 0, stream>>>(a);
+    tile_matvec_reduce_kernel<<<a.nt + (a.op != 0 ? 1 : 0), 512, 0, stream>>>(a);
     return cudaGetLastError();
 }
 
