@@ -256,7 +256,8 @@ struct cheq_ctx {
         lu_f, lu_piv, sgn, sgn_flags, xsol;
     // stale-factor SCF iterations (kernels_krylov.cu): explicit R = L_hh^-T S of the frozen hydrogen factor, partial
     // sums of the tiled matrix-vector products, the small vectors of GMRES, device / pinned-host scalars
-    DeviceBuffer kr_R, kr_part, kr_vec, kr_sc;
+    DeviceBuffer kr_R, kr_Rf, kr_part, kr_vec, kr_sc;
+    int krylov_f32 = 1;               // CHEQ_KRYLOV_F32=0: apply the frozen factor from the fp64 R
     KrylovScalars* h_ksc = nullptr;   // pinned
     int morton = 1;                   // CHEQ_MORTON=0: atoms of one element stay in input order (test knob: a
                                       // different elimination order for the unpivoted factorisation)
@@ -1256,6 +1257,7 @@ struct Krylov {
     int nhp = 0, nt = 0, len = 0;               // len = nhp + 1 entries per vector
     long vs = 0;                                // vector stride (doubles)
     double *R = nullptr, *partN = nullptr, *partT = nullptr;
+    float* Rf = nullptr;                        // single-precision copy of R used by the preconditioner (shifted base like R)
     double *tc = nullptr, *t1 = nullptr, *ws = nullptr, *d_cur = nullptr, *d_prev = nullptr, *d_frozen = nullptr,
            *sol = nullptr, *r = nullptr, *z = nullptr, *tmp1 = nullptr, *tmp2 = nullptr, *w = nullptr, *V = nullptr;
     KrylovScalars* sc = nullptr;
@@ -1299,6 +1301,7 @@ int krylov_alloc(cheq_ctx* ctx, Krylov& K, int nhp, bool dist) {
     }
     const size_t r_rows = (size_t)std::max(1, K.rb - K.ra) * kTile;
     CU(ctx->kr_R.ensure(r_rows * nhp * 8));
+    if (ctx->krylov_f32) CU(ctx->kr_Rf.ensure(r_rows * nhp * 4));
     CU(ctx->kr_part.ensure((size_t)2 * K.nt * K.nt * kTile * 8));
     const size_t nvec = 12 + Krylov::kMaxBasis + 1;
     CU(ctx->kr_vec.ensure(nvec * K.vs * 8));
@@ -1306,6 +1309,7 @@ int krylov_alloc(cheq_ctx* ctx, Krylov& K, int nhp, bool dist) {
     if (!ctx->h_ksc) CU(cudaMallocHost((void**)&ctx->h_ksc, sizeof(KrylovScalars)));
     // R is addressed with GLOBAL tile-row indices: the base is shifted up by the rows this rank does not hold
     K.R = ctx->kr_R.as<double>() - (long)K.ra * kTile;
+    K.Rf = ctx->krylov_f32 ? ctx->kr_Rf.as<float>() - (long)K.ra * kTile : nullptr;
     K.partN = ctx->kr_part.as<double>();
     K.partT = K.partN + (size_t)K.nt * K.nt * kTile;
     double* v = ctx->kr_vec.as<double>();
@@ -1325,7 +1329,8 @@ int krylov_alloc(cheq_ctx* ctx, Krylov& K, int nhp, bool dist) {
 int krylov_apply_sinv(cheq_ctx* ctx, Krylov& K, const double* in, double* out) {
     cudaStream_t st = ctx->stream;
     TileMatvecArgs a{};
-    a.M = K.R;
+    a.M = K.Rf ? (const void*)K.Rf : (const void*)K.R;
+    a.f32 = K.Rf ? 1 : 0;
     a.ld = (long)(K.rb - K.ra) * kTile;
     a.nt = K.nt;
     a.upper = 1;
@@ -1360,7 +1365,7 @@ int krylov_apply_sinv(cheq_ctx* ctx, Krylov& K, const double* in, double* out) {
         CU(cudaMemsetAsync(out + K.nhp, 0, sizeof(double), st));
         if (int rc = krylov_allreduce(ctx, K, out)) return rc;
     }
-    K.bytes += 8.0 * (double)K.nhp * (K.nhp + 1.0) / (K.dist ? ctx->world : 1);
+    K.bytes += (K.Rf ? 4.0 : 8.0) * (double)K.nhp * (K.nhp + 1.0) / (K.dist ? ctx->world : 1);
     return CHEQ_OK;
 }
 
@@ -1462,6 +1467,9 @@ int krylov_freeze(cheq_ctx* ctx, Dense& D, Krylov& K, int nxp, const double* d_o
     int rc = krylov_build_R(D, K, nxp, 0, K.nhp);
     if (rc) return rc;
     CU(cudaMemcpyAsync(K.d_frozen, d_of_factor, (size_t)K.nhp * 8, cudaMemcpyDeviceToDevice, st));
+    if (K.Rf)
+        LAUNCH(launch_convert_upper_tiles_f32(K.R + (long)K.ra * kTile, K.Rf + (long)K.ra * kTile,
+                                              (long)(K.rb - K.ra) * kTile, K.nt, K.ra, K.rb, st));
     rc = krylov_apply_sinv(ctx, K, K.t1, K.ws);
     if (rc) return rc;
     LAUNCH(launch_precond_den(K.t1, K.ws, K.sc, K.nhp, st));
@@ -1482,6 +1490,10 @@ struct GmresWork {
     double *r = nullptr, *z = nullptr, *w = nullptr, *V = nullptr;   // device: residual, P r, work vector, basis [m][vs]
     KrylovScalars* sc = nullptr; // device
     double stall_accept = 1e3;   // a stalled restart is accepted if |P r| <= stall_accept * tol * scale
+    // Strong preconditioners (frozen exact factor): a cycle that ends because the recurrence's residual estimate fell
+    // below trust_margin * tol * scale is accepted without recomputing the true residual (the Arnoldi relation holds to
+    // rounding with twice-applied Gram-Schmidt; one operator application saved per SCF iteration).  0: always verify.
+    double trust_margin = 0.0;
 };
 
 template <class ApplyK, class ApplyP>
@@ -1566,7 +1578,8 @@ int gmres_solve(cheq_ctx* ctx, const GmresWork& G, ApplyK&& apply_K, ApplyP&& ap
             gv[j] = cs[j] * gv[j];
             k = j + 1;
             if (debug) fprintf(stderr, "[gmres]   step %d  estimate %.3e\n", j, std::fabs(gv[j + 1]));
-            if (std::fabs(gv[j + 1]) <= 0.3 * tol * scale || *steps >= G.max_steps) break;
+            if (std::fabs(gv[j + 1]) <= (G.trust_margin > 0.0 ? G.trust_margin : 0.3) * tol * scale || *steps >= G.max_steps)
+                break;
         }
         if (k == 0) return CHEQ_OK;
         for (int i = k - 1; i >= 0; --i) {
@@ -1577,6 +1590,10 @@ int gmres_solve(cheq_ctx* ctx, const GmresWork& G, ApplyK&& apply_K, ApplyP&& ap
         for (int i = 0; i < k; ++i) hs->y[i] = y[i];
         CU(cudaMemcpyAsync(G.sc->y, hs->y, k * sizeof(double), cudaMemcpyHostToDevice, st));
         LAUNCH(launch_combine(G.V, G.vs, sol, G.len, G.sc->y, k, st));
+        if (G.trust_margin > 0.0 && std::fabs(gv[k]) <= G.trust_margin * tol * scale) {
+            *ok = true;
+            return CHEQ_OK;
+        }
     }
     return CHEQ_OK;
 }
@@ -1595,6 +1612,7 @@ int krylov_solve(cheq_ctx* ctx, Krylov& K, double tol, int* steps, bool* ok) {
     G.w = K.w;
     G.V = K.V;
     G.sc = K.sc;
+    G.trust_margin = 0.1;
     return gmres_solve(
         ctx, G, [&](const double* v, double* out) { return krylov_apply_K(ctx, K, v, out, 1); },
         [&](const double* in, double* out) { return krylov_apply_precond(ctx, K, in, out); }, K.tc, K.sol, tol, steps, ok);
@@ -2677,6 +2695,7 @@ int32_t cheq_ctx_create(int32_t device, cheq_ctx** out) {
     if (const char* env = getenv("CHEQ_MATFREE_MAX_STEPS")) ctx->matfree_max_steps = std::max(10, atoi(env));
     if (const char* env = getenv("CHEQ_MATFREE_TOL")) ctx->matfree_tol = atof(env);
     if (const char* env = getenv("CHEQ_KRYLOV")) ctx->krylov_mode = atoi(env) != 0;
+    if (const char* env = getenv("CHEQ_KRYLOV_F32")) ctx->krylov_f32 = atoi(env) != 0;
     if (const char* env = getenv("CHEQ_KRYLOV_MIN_NH")) ctx->krylov_min_nhp = std::max(128, atoi(env));
     if (const char* env = getenv("CHEQ_KRYLOV_FREEZE_EV")) ctx->krylov_freeze_ev = atof(env);
     if (const char* env = getenv("CHEQ_KRYLOV_FORCE_IT")) ctx->krylov_force_it = std::max(2, atoi(env));
@@ -2727,6 +2746,7 @@ void cheq_ctx_destroy(cheq_ctx* ctx) {
         ctx->mf = nullptr;
     }
     ctx->kr_R.release();
+    ctx->kr_Rf.release();
     ctx->kr_part.release();
     ctx->kr_vec.release();
     ctx->kr_sc.release();

@@ -187,7 +187,8 @@ struct KrylovScalars {
 };
 
 struct TileMatvecArgs {
-    const double* M;   // nt x nt tiles of 128, column-major
+    const void* M;     // nt x nt tiles of 128, column-major; doubles, or floats when f32 != 0
+    int f32;
     long ld;
     int nt;
     int upper;         // 0: tiles i >= j hold the data (lower), 1: tiles i <= j (upper)
@@ -219,6 +220,9 @@ struct TileReduceArgs {
 
 cudaError_t launch_tile_matvec(const TileMatvecArgs& a, bool do_n, bool do_t, cudaStream_t stream);
 cudaError_t launch_tile_matvec_reduce(const TileReduceArgs& a, cudaStream_t stream);
+// R and Rf point at the first LOCAL tile row (global tile row row_begin)
+cudaError_t launch_convert_upper_tiles_f32(const double* R, float* Rf, long ld, int nt, int row_begin, int row_end,
+                                           cudaStream_t stream);
 cudaError_t launch_multi_dot(const double* V, long stride, const double* w, int len, double* out, int m,
                              bool with_norm, cudaStream_t stream);
 cudaError_t launch_gs_update(const double* V, long stride, double* w, int len, const double* h, double* hsum, int m,

@@ -32,7 +32,7 @@ namespace {
 // Diagonal tiles are masked to the stored triangle; `sym` (symmetric matrix stored as its lower triangle) counts the
 // diagonal itself only in the N product.
 // ---------------------------------------------------------------------------------------------------------------
-template <bool DO_N, bool DO_T>
+template <bool DO_N, bool DO_T, class T_ELEM>
 __global__ void __launch_bounds__(256)
 tile_matvec_kernel(TileMatvecArgs a) {
     const int j = blockIdx.y;
@@ -51,7 +51,9 @@ tile_matvec_kernel(TileMatvecArgs a) {
     if (a.upper ? (i > j) : (i >= a.nt)) return;
     if (a.row_end > 0 && (i < a.row_begin || i >= a.row_end)) return;   // tile row held by another rank
     const bool diag = (i == j);
-    const double* T = a.M + (long)i * kTile + (long)j * kTile * a.ld + lane;
+    // T_ELEM = float: the preconditioner's R is kept in single precision (half the bytes; GMRES only needs a FIXED
+    // linear operator close to K_s^-1, the residuals that decide convergence are formed with the fp64 S0)
+    const T_ELEM* T = (const T_ELEM*)a.M + (long)i * kTile + (long)j * kTile * a.ld + lane;
     double xt[4] = {0.0, 0.0, 0.0, 0.0};
     if (DO_T) {
 #pragma unroll
@@ -66,10 +68,10 @@ tile_matvec_kernel(TileMatvecArgs a) {
     double keepT = 0.0;
 #pragma unroll 4
     for (int c = 0; c < kTile; ++c) {
-        const double* p = T + (long)c * a.ld;
+        const T_ELEM* p = T + (long)c * a.ld;
         double t[4];
 #pragma unroll
-        for (int m = 0; m < 4; ++m) t[m] = __ldg(p + 32 * m);   // default caching: a 3,000-atom system's S0 and R live in L2
+        for (int m = 0; m < 4; ++m) t[m] = (double)__ldg(p + 32 * m);   // default caching: a 3,000-atom system's S0 and R live in L2
         if (diag) {
 #pragma unroll
             for (int m = 0; m < 4; ++m) {
@@ -421,9 +423,36 @@ cudaError_t launch_matfree_unpack(const double* sol, int NP, double* x, ScfState
 // ---------------------------------------------------------------------------------------------------------------
 cudaError_t launch_tile_matvec(const TileMatvecArgs& a, bool do_n, bool do_t, cudaStream_t stream) {
     dim3 grid((a.nt + 7) / 8, a.nt);
-    if (do_n && do_t) tile_matvec_kernel<true, true><<<grid, 256, 0, stream>>>(a);
-    else if (do_n) tile_matvec_kernel<true, false><<<grid, 256, 0, stream>>>(a);
-    else tile_matvec_kernel<false, true><<<grid, 256, 0, stream>>>(a);
+    if (a.f32) {
+        if (do_n && do_t) tile_matvec_kernel<true, true, float><<<grid, 256, 0, stream>>>(a);
+        else if (do_n) tile_matvec_kernel<true, false, float><<<grid, 256, 0, stream>>>(a);
+        else tile_matvec_kernel<false, true, float><<<grid, 256, 0, stream>>>(a);
+    } else {
+        if (do_n && do_t) tile_matvec_kernel<true, true, double><<<grid, 256, 0, stream>>>(a);
+        else if (do_n) tile_matvec_kernel<true, false, double><<<grid, 256, 0, stream>>>(a);
+        else tile_matvec_kernel<false, true, double><<<grid, 256, 0, stream>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+// upper tiles (i <= j) of the local rows of R: double -> float, same leading dimension (in elements)
+__global__ void __launch_bounds__(256)
+convert_upper_tiles_f32_kernel(const double* R, float* Rf, long ld, int row_begin, int row_end) {
+    const int ti = row_begin + blockIdx.x, tj = blockIdx.y;
+    if (ti >= row_end || ti > tj) return;
+    const long off = (long)(ti - row_begin) * kTile + (long)tj * kTile * ld;
+    for (int idx = threadIdx.x; idx < kTile * kTile / 2; idx += 256) {
+        const int r2 = idx & 63, c = idx >> 6;
+        const double2 v = *(const double2*)(R + off + 2 * r2 + (long)c * ld);
+        *(float2*)(Rf + off + 2 * r2 + (long)c * ld) = make_float2((float)v.x, (float)v.y);
+    }
+}
+
+cudaError_t launch_convert_upper_tiles_f32(const double* R, float* Rf, long ld, int nt, int row_begin, int row_end,
+                                           cudaStream_t stream) {
+    if (row_end <= row_begin) return cudaSuccess;
+    dim3 grid(row_end - row_begin, nt);
+    convert_upper_tiles_f32_kernel<<<grid, 256, 0, stream>>>(R, Rf, ld, row_begin, row_end);
     return cudaGetLastError();
 }
 
