@@ -2010,8 +2010,9 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
         // must take the same decision, and they do: same sizes, same device type, same allocations so far
         size_t free_b = 0, total_b = 0;
         CU(cudaMemGetInfo(&free_b, &total_b));
-        const size_t need = (size_t)L.nhp * L.nhp * 8 / (dist ? 2 : 1) + ((size_t)256 << 20);
-        if (need > free_b + ctx->kr_R.cap) kry = false;
+        const size_t need = (size_t)L.nhp * L.nhp * (ctx->krylov_f32 ? 12 : 8) / (dist ? 2 : 1) + ((size_t)256 << 20);
+        const size_t have_r = ctx->kr_R.cap + ctx->kr_Rf.cap;
+        if (need > free_b + have_r) kry = false;
         if (dist) {
             int* flag = ctx->ipc_stage.as<int>() + 32;
             const int mine = kry ? 1 : 0;

@@ -52,6 +52,22 @@ extern "C" {
         external: *const cheq_external, charges_out: *mut f64, potential_out: *mut f64,
         iterations_out: *mut u32, delta_out: *mut f64,
     ) -> i32;
+    /// Same solve without ever forming the (N + 1)^2 matrix (restarted GMRES, tiles recomputed on the fly).
+    pub fn cheq_solve_iterative(
+        ctx: *mut cheq_ctx, n_atoms: u64, xyz: *const f64, chi: *const f64, hardness: *const f64,
+        radius: *const f64, n_quantum: *const u8, total_charge: f64, options: *const cheq_options,
+        external: *const cheq_external, charges_out: *mut f64, potential_out: *mut f64,
+        iterations_out: *mut u32, delta_out: *mut f64,
+    ) -> i32;
+    /// Per-iteration trace of the last single-frame solve (max-abs charge change, solve mode, GMRES steps).
+    pub fn cheq_get_scf_trace(
+        ctx: *const cheq_ctx, capacity: u32, delta_out: *mut f64, mode_out: *mut i32, steps_out: *mut i32,
+        count_out: *mut u32,
+    ) -> i32;
+    /// Stale-factor policy of the hydrogen SCF iterations (0 = refactor every iteration).
+    pub fn cheq_set_krylov(
+        ctx: *mut cheq_ctx, enabled: i32, min_hydrogen: i32, freeze_ev: f64, force_iteration: i32,
+    ) -> i32;
     pub fn cheq_solve_batch(
         ctx: *mut cheq_ctx, n_frames: u64, n_atoms: u64, xyz: *const f64, chi: *const f64,
         hardness: *const f64, radius: *const f64, n_quantum: *const u8, total_charge: f64,
