@@ -1507,6 +1507,7 @@ int gmres_solve(cheq_ctx* ctx, const GmresWork& G, ApplyK&& apply_K, ApplyP&& ap
     *steps = 0;
     *ok = false;
     static const bool debug = [] { const char* e = getenv("CHEQ_KRYLOV_DEBUG"); return e && e[0] == '1'; }();
+    const auto t_begin = Clock::now();
     double scale = 0.0, beta_prev = 0.0;
     for (int cycle = 0; cycle < 64; ++cycle) {
         // true residual, preconditioned: z = P (b - K sol)
@@ -1525,7 +1526,8 @@ int gmres_solve(cheq_ctx* ctx, const GmresWork& G, ApplyK&& apply_K, ApplyP&& ap
             scale = std::sqrt(hs->dots[1]);
             if (!(scale > 0.0)) scale = std::max(beta, 1e-300);   // zero initial guess: measure against the first correction
         }
-        if (debug) fprintf(stderr, "[gmres] cycle %d steps %d  |P r| = %.3e  scale = %.3e\n", cycle, *steps, beta, scale);
+        if (debug && ctx->rank == 0)
+            fprintf(stderr, "[gmres %.3f ms] cycle %d steps %d  |P r| = %.3e  scale = %.3e\n", ms_since(t_begin), cycle, *steps, beta, scale);
         if (!std::isfinite(beta)) return CHEQ_OK;                        // not ok
         if (beta <= tol * scale) {
             *ok = true;
@@ -1577,7 +1579,8 @@ int gmres_solve(cheq_ctx* ctx, const GmresWork& G, ApplyK&& apply_K, ApplyP&& ap
             gv[j + 1] = -sn[j] * gv[j];
             gv[j] = cs[j] * gv[j];
             k = j + 1;
-            if (debug) fprintf(stderr, "[gmres]   step %d  estimate %.3e\n", j, std::fabs(gv[j + 1]));
+            if (debug && ctx->rank == 0)
+                fprintf(stderr, "[gmres %.3f ms]   step %d  estimate %.3e\n", ms_since(t_begin), j, std::fabs(gv[j + 1]));
             if (std::fabs(gv[j + 1]) <= (G.trust_margin > 0.0 ? G.trust_margin : 0.3) * tol * scale || *steps >= G.max_steps)
                 break;
         }
