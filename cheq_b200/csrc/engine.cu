@@ -256,7 +256,9 @@ struct cheq_ctx {
         lu_f, lu_piv, sgn, sgn_flags, xsol;
     // stale-factor SCF iterations (kernels_krylov.cu): explicit R = L_hh^-T S of the frozen hydrogen factor, partial
     // sums of the tiled matrix-vector products, the small vectors of GMRES, device / pinned-host scalars
-    DeviceBuffer kr_R, kr_Rf, kr_part, kr_vec, kr_sc;
+    DeviceBuffer kr_R, kr_Rf, kr_part, kr_vec, kr_sc, kr_wx, kx_local;
+    unsigned kx_seq = 0;              // rounds of the peer-memory all-reduce so far (identical on every rank)
+    int krylov_p2p = 1;               // CHEQ_KRYLOV_P2P=0: ncclAllReduce instead of the peer-memory all-reduce
     int krylov_f32 = 1;               // CHEQ_KRYLOV_F32=0: apply the frozen factor from the fp64 R
     KrylovScalars* h_ksc = nullptr;   // pinned
     int morton = 1;                   // CHEQ_MORTON=0: atoms of one element stay in input order (test knob: a
@@ -964,14 +966,19 @@ int ensure_panel_plan(cheq_ctx* ctx, const Layout& L) {
 // ---- peer-memory data plane ----------------------------------------------------------------------------------
 // Layout of the arena for a padded size NP: signal words, then Linv (NP x 128), sgn (NP), negative-pivot counts
 // (NP / 128) and lists (NP).  Identical on every rank, so a local offset is also the peer's offset.
+// Round 2: + the inboxes of the peer-memory all-reduce of the stale-factor iterations (kernels_krylov.cu): flag words
+// at byte 1024 of the signal page (2 parities x 16 ranks), data = 2 parities x 8 rank slots x (NP + 8) doubles.
 struct ArenaLayout {
-    size_t linv, sgn, neg_cnt, neg_idx, bytes;
+    size_t linv, sgn, neg_cnt, neg_idx, kx_data, kx_slot, bytes;
+    static constexpr size_t kx_flags = 1024;
     explicit ArenaLayout(long NP) {
         linv = 4096;
         sgn = linv + (size_t)NP * kTile * 8;
         neg_cnt = sgn + (size_t)NP * 8;
         neg_idx = neg_cnt + (((size_t)(NP / kTile) * 4 + 255) / 256) * 256;
-        bytes = neg_idx + (size_t)NP * 4;
+        kx_data = ((neg_idx + (size_t)NP * 4 + 255) / 256) * 256;
+        kx_slot = (size_t)NP + 8;
+        bytes = kx_data + 2 * (size_t)(kMaxPeers + 1) * kx_slot * 8;
         bytes = std::max<size_t>(bytes, (size_t)8 << 20);   // its own allocation, never a sub-allocation
     }
 };
@@ -1272,14 +1279,40 @@ struct Krylov {
     bool dist = false;
     const uint8_t* col_mask = nullptr;
     int ra = 0, rb = 0;
+    bool p2p = false;                           // all-reduces go through the peer-mapped arenas
+    size_t kx_data = 0, kx_slot = 0;            // ArenaLayout of the current solve
 };
 
-// sums the (n + 1)-vector over the ranks of the group (identical result on every rank)
-int krylov_allreduce(cheq_ctx* ctx, const Krylov& K, double* v) {
+// sums a vector over the ranks of the group (identical result on every rank): through the peer-mapped arenas when
+// the NVLink mappings are up (one push + one combine kernel, ~10 us), else ncclAllReduce (~55 us on 8 GPUs)
+int krylov_allreduce_n(cheq_ctx* ctx, const Krylov& K, double* v, int len) {
     if (!K.dist) return CHEQ_OK;
-    NC(g_nccl.AllReduce(v, v, (size_t)K.len, kNcclDouble, 0 /* ncclSum */, ctx->comm, ctx->stream));
+    if (K.p2p) {
+        const cheq_ctx::PeerLinks& lk = ctx->links;
+        P2PAllreduce pa{};
+        pa.world = ctx->world;
+        pa.rank = ctx->rank;
+        pa.slot = (long)K.kx_slot;
+        pa.seq = ++ctx->kx_seq;
+        const size_t par = pa.seq & 1u;
+        for (int d = 0; d < ctx->world; ++d) {
+            char* base = nullptr;
+            if (d == ctx->rank) base = ctx->arena.as<char>();
+            else
+                for (int i = 0; i < lk.n; ++i)
+                    if (lk.rank_of[i] == d) base = lk.arena[i];
+            if (!base) return fail(ctx, CHEQ_ERR_CUDA, "peer arena of a rank is not mapped");
+            pa.inbox[d] = (double*)(base + K.kx_data) + par * (size_t)(kMaxPeers + 1) * K.kx_slot;
+            pa.flags[d] = (unsigned*)(base + ArenaLayout::kx_flags) + par * 16;
+        }
+        LAUNCH(launch_p2p_allreduce(v, v, len, pa, ctx->kx_local.as<unsigned>(), ctx->kx_local.as<int>() + 1, ctx->stream));
+        ctx->launches++;
+        return CHEQ_OK;
+    }
+    NC(g_nccl.AllReduce(v, v, (size_t)len, kNcclDouble, 0 /* ncclSum */, ctx->comm, ctx->stream));
     return CHEQ_OK;
 }
+int krylov_allreduce(cheq_ctx* ctx, const Krylov& K, double* v) { return krylov_allreduce_n(ctx, K, v, K.len); }
 
 int krylov_alloc(cheq_ctx* ctx, Krylov& K, int nhp, bool dist) {
     K.nhp = nhp;
@@ -2034,6 +2067,14 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
         K.ld0 = ld0;
         K.sgn_h = D.sgn + L.nxp;
         K.col_mask = mask_h;
+        if (dist) {
+            const ArenaLayout AL(L.NP);
+            K.kx_data = AL.kx_data;
+            K.kx_slot = AL.kx_slot;
+            K.p2p = ctx->krylov_p2p && ctx->links.enabled && ctx->arena.cap >= AL.bytes;
+            CU(ctx->kx_local.ensure(64));
+            CU(cudaMemsetAsync(ctx->kx_local.p, 0, 64, st));
+        }
         LAUNCH(launch_krylov_setup(D.A, D.ld, L.NP, L.nxp, D.sgn, K.S0, ld0, L.nhp, io.total_charge, K.sc, K.tc, K.t1,
                                    mask_h, (!dist || ctx->rank == 0) ? 1 : 0, st));
         if (dist) {
@@ -2085,12 +2126,37 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
             bool ok = false;
             rc = krylov_solve(ctx, K, 1e-13, &gm_steps, &ok);
             if (rc) return rc;
+            if (K.p2p) {
+                int kx_err = 0;
+                CU(cudaMemcpyAsync(&kx_err, ctx->kx_local.as<int>() + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+                CU(cudaStreamSynchronize(st));
+                if (kx_err) return fail(ctx, CHEQ_ERR_CUDA, "peer-memory all-reduce timed out waiting for a rank");
+            }
             if (ok) {
-                LAUNCH(launch_krylov_finish(D.A, D.ld, L.NP, L.nxp, K.sol, L.nhp, v, xs, D.state, st));
+                // x_x = L_xx^-T (S (yc_x - mu y1_x) - W^T x_h): the hydrogen part W^T x_h is one HBM-speed pass over
+                // W = L[hydrogen rows, non-hydrogen columns] (split by row chunks over the ranks of a group), then the
+                // back-substitution chain runs over the non-hydrogen blocks only
                 if (int rcp = prof_begin(ctx, 2)) return rcp;
+                const int nth = L.nhp / kTile, ntx = L.nxp / kTile;
+                double* wx = nullptr;
+                if (ntx > 0) {
+                    CU(ctx->kr_wx.ensure((size_t)(nth + 1) * ntx * kTile * 8 + (size_t)(L.nxp + 8) * 8));
+                    double* wpart = ctx->kr_wx.as<double>();
+                    wx = wpart + (size_t)nth * ntx * kTile;
+                    int wb = 0, we = nth;
+                    if (dist) {
+                        wb = (int)((long)nth * ctx->rank / ctx->world);
+                        we = (int)((long)nth * (ctx->rank + 1) / ctx->world);
+                    }
+                    LAUNCH(launch_rect_matvec_t(D.A + L.nxp, D.ld, nth, ntx, wb, we, K.sol, wpart, wx, st));
+                    if (dist)
+                        if (int rca = krylov_allreduce_n(ctx, K, wx, L.nxp)) return rca;
+                    K.bytes += 8.0 * (double)L.nhp * L.nxp / (dist ? ctx->world : 1);
+                }
+                LAUNCH(launch_krylov_finish(D.A, D.ld, L.NP, L.nxp, K.sol, L.nhp, v, xs, D.state, wx, st));
                 CU(ctx->chain.ensure((size_t)(L.NP / kTile + 1) * sizeof(unsigned)));
-                LAUNCH(launch_backsolve_chain(D.A, D.ld, D.strideA, D.Linv, D.strideLinv, D.sgn, D.strideSgn, L.NP, v,
-                                              xs, L.NP, ctx->chain.as<unsigned>(), D.state, 1, st, L.nxp / kTile));
+                LAUNCH(launch_backsolve_chain(D.A, D.ld, D.strideA, D.Linv, D.strideLinv, D.sgn, D.strideSgn, L.nxp, v,
+                                              xs, L.NP, ctx->chain.as<unsigned>(), D.state, 1, st));
                 if (int rcp = prof_end(ctx)) return rcp;
             } else {
                 // GMRES did not reach the target with this factor: refactor at the current shift instead
@@ -2700,6 +2766,7 @@ int32_t cheq_ctx_create(int32_t device, cheq_ctx** out) {
     if (const char* env = getenv("CHEQ_MATFREE_TOL")) ctx->matfree_tol = atof(env);
     if (const char* env = getenv("CHEQ_KRYLOV")) ctx->krylov_mode = atoi(env) != 0;
     if (const char* env = getenv("CHEQ_KRYLOV_F32")) ctx->krylov_f32 = atoi(env) != 0;
+    if (const char* env = getenv("CHEQ_KRYLOV_P2P")) ctx->krylov_p2p = atoi(env) != 0;
     if (const char* env = getenv("CHEQ_KRYLOV_MIN_NH")) ctx->krylov_min_nhp = std::max(128, atoi(env));
     if (const char* env = getenv("CHEQ_KRYLOV_FREEZE_EV")) ctx->krylov_freeze_ev = atof(env);
     if (const char* env = getenv("CHEQ_KRYLOV_FORCE_IT")) ctx->krylov_force_it = std::max(2, atoi(env));
@@ -2751,6 +2818,8 @@ void cheq_ctx_destroy(cheq_ctx* ctx) {
     }
     ctx->kr_R.release();
     ctx->kr_Rf.release();
+    ctx->kr_wx.release();
+    ctx->kx_local.release();
     ctx->kr_part.release();
     ctx->kr_vec.release();
     ctx->kr_sc.release();

@@ -218,6 +218,17 @@ struct TileReduceArgs {
     double* out;
 };
 
+// All-reduce of a short vector over peer memory (see kernels_krylov.cu).  inbox[d] / flags[d]: rank d's inbox base
+// (for the buffer of this round's parity) and flag words as mapped into THIS process; d == rank is local memory.
+struct P2PAllreduce {
+    int world, rank;
+    long slot;                 // doubles per rank slot
+    unsigned seq;              // sequence number of this round (the same on every rank)
+    double* inbox[kMaxPeers + 1];
+    unsigned* flags[kMaxPeers + 1];
+};
+cudaError_t launch_p2p_allreduce(const double* src, double* out, int len, const P2PAllreduce& pa, unsigned* done_counter,
+                                 int* error, cudaStream_t stream);
 cudaError_t launch_tile_matvec(const TileMatvecArgs& a, bool do_n, bool do_t, cudaStream_t stream);
 cudaError_t launch_tile_matvec_reduce(const TileReduceArgs& a, cudaStream_t stream);
 // R and Rf point at the first LOCAL tile row (global tile row row_begin)
@@ -241,8 +252,12 @@ cudaError_t launch_krylov_setup(const double* A, long lda, int NP, int nxp, cons
 cudaError_t launch_h_shift(const double* hard_h, const double* q_h, const uint8_t* type_h, int nhp, double* d_new,
                            const double* d_ref, KrylovScalars* sc, cudaStream_t stream);
 cudaError_t launch_set_identity_tiles(double* R, long ld, int nt, int row_begin, int row_end, cudaStream_t stream);
+// wx (nullable): W^T x_h, already subtracted from the right-hand side of the non-hydrogen back substitution
 cudaError_t launch_krylov_finish(const double* A, long lda, int NP, int nxp, const double* sol, int nhp, double* v,
-                                 double* x, ScfState* state, cudaStream_t stream);
+                                 double* x, ScfState* state, const double* wx, cudaStream_t stream);
+// out[nt_cols * 128] = sum over the tile rows [row_begin, row_end) of M(i, j)^T x_i; M: nt_rows x nt_cols tiles, ld
+cudaError_t launch_rect_matvec_t(const double* M, long ld, int nt_rows, int nt_cols, int row_begin, int row_end,
+                                 const double* x, double* part, double* out, cudaStream_t stream);
 cudaError_t launch_krylov_capture(const double* x, int nxp, int nhp, const ScfState* state, double* sol,
                                   cudaStream_t stream);
 

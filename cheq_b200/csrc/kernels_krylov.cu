@@ -108,6 +108,112 @@ tile_matvec_kernel(TileMatvecArgs a) {
     }
 }
 
+// Rectangular product  out[col block j] = sum_i T(i, j)^T x[row block i]  over ALL tiles of an nt_rows x nt_cols tile
+// matrix (W = L[hydrogen rows, non-hydrogen columns]: the hydrogen part of the back substitution's right-hand side,
+// streamed at HBM speed instead of by the chain CTAs).  Same warp-per-tile scheme as tile_matvec_kernel, T mode;
+// partials part[(j * nt_rows + i) * 128 + c], rows [row_begin, row_end) only (the ranks of a group split the rows).
+__global__ void __launch_bounds__(256)
+rect_matvec_t_kernel(const double* M, long ld, int nt_rows, int row_begin, int row_end, const double* x, double* part) {
+    const int j = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int i = row_begin + blockIdx.x * 8 + warp;
+    if (i >= row_end) return;
+    const double* T = M + (long)i * kTile + (long)j * kTile * ld + lane;
+    double xt[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) xt[m] = x[i * kTile + lane + 32 * m];
+    double* out = part + ((long)j * nt_rows + i) * kTile;
+    double keep = 0.0;
+#pragma unroll 4
+    for (int c = 0; c < kTile; ++c) {
+        const double* p = T + (long)c * ld;
+        double s = __ldg(p) * xt[0];
+        s = fma(__ldg(p + 32), xt[1], s);
+        s = fma(__ldg(p + 64), xt[2], s);
+        s = fma(__ldg(p + 96), xt[3], s);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+        if ((c & 31) == lane) keep = s;
+        if ((c & 31) == 31) out[c - 31 + lane] = keep;
+    }
+}
+
+// out[j * 128 + r] = sum_{i in [row_begin, row_end)} part[(j * nt_rows + i) * 128 + r]   (fixed order, 4 groups)
+__global__ void __launch_bounds__(512)
+rect_matvec_reduce_kernel(const double* part, int nt_rows, int row_begin, int row_end, double* out) {
+    const int j = blockIdx.x, r = threadIdx.x & 127, g = threadIdx.x >> 7;
+    __shared__ double red[4][128];
+    double s = 0.0;
+    for (int i = row_begin + g; i < row_end; i += 4) s += part[((long)j * nt_rows + i) * kTile + r];
+    red[g][r] = s;
+    __syncthreads();
+    if (g == 0) out[j * kTile + r] = (red[0][r] + red[1][r]) + (red[2][r] + red[3][r]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// All-reduce of a short vector (n_h + 1 doubles) over NVLink / NVSwitch PEER MEMORY: three of these per GMRES step on
+// a group, where ncclAllReduce costs ~55 us each (measured: 0.41 ms per step on 8 GPUs with 0.045 ms of streaming).
+//   push:    every rank stores its partial vector into slot [rank] of the inbox of EVERY rank (its own included;
+//            the inboxes live in the peer-mapped arenas), fences at system scope, and the last CTA to finish
+//            release-stores the sequence number into that rank's flag word on every destination;
+//   combine: waits until all `world` flags of the local inbox carry the sequence number, then sums the slots in rank
+//            order -- the same operands in the same order on every rank, so the result is bit-identical everywhere.
+// Two inboxes alternate by sequence parity: a rank can only push round s + 2 after its combine of round s + 1, which
+// needed every peer's push of round s + 1, issued after that peer's combine of round s.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+p2p_push_kernel(const double* src, int len, P2PAllreduce pa, unsigned* done_counter) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < len) {
+        const double v = src[i];
+        for (int d = 0; d < pa.world; ++d) pa.inbox[d][(long)pa.rank * pa.slot + i] = v;
+    }
+    __threadfence_system();
+    __shared__ int last;
+    __syncthreads();
+    if (threadIdx.x == 0) last = (atomicAdd(done_counter, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (last) {
+        __threadfence_system();
+        if (threadIdx.x < pa.world) {
+            volatile unsigned* f = pa.flags[threadIdx.x] + pa.rank;
+            *f = pa.seq;
+        }
+        if (threadIdx.x == 0) *done_counter = 0u;   // ready for the next push on this stream
+        __threadfence_system();
+    }
+}
+
+__global__ void __launch_bounds__(256)
+p2p_combine_kernel(P2PAllreduce pa, int len, double* out, int* error) {
+    __shared__ int ok_s;
+    if (threadIdx.x == 0) {
+        volatile unsigned* f = pa.flags[pa.rank];
+        int ok = 1;
+        const long long t0 = clock64();
+        for (int s = 0; s < pa.world; ++s) {
+            // wrap-safe "flag >= seq"
+            while ((int)(f[s] - pa.seq) < 0) {
+                if (clock64() - t0 > 4000000000ll) {   // ~2 s: a peer never arrived -- report instead of hanging
+                    ok = 0;
+                    break;
+                }
+            }
+            if (!ok) break;
+        }
+        if (!ok) atomicExch(error, 1);
+        ok_s = ok;
+    }
+    __syncthreads();
+    __threadfence_system();
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= len) return;
+    const double* in = pa.inbox[pa.rank];
+    double s = 0.0;
+    for (int r = 0; r < pa.world; ++r) s += __ldcg(in + (long)r * pa.slot + i);
+    out[i] = ok_s ? s : nan("");
+}
+
 // One CTA per 128-row block b: fixed-order sum of the partials that belong to it, then the epilogue of the
 // operator being applied.  Block nt (one extra CTA) computes the border entry.
 //   op 0: out = sum                                   (triangular passes)
@@ -346,14 +452,15 @@ set_identity_tiles_kernel(double* R, long ld, int nt, int row_begin, int row_end
     }
 }
 
-// v_x = yc_x - mu y1_x for the non-hydrogen columns, x_h copied into the solution vector, state.mu = mu
+// v_x = yc_x - mu y1_x (- W^T x_h if wx is given) for the non-hydrogen columns, x_h copied into the solution vector,
+// state.mu = mu
 __global__ void __launch_bounds__(256)
 krylov_finish_kernel(const double* A, long lda, int NP, int nxp, const double* sol, int nhp, double* v, double* x,
-                     ScfState* state) {
+                     ScfState* state, const double* wx) {
     const int i = blockIdx.x * 256 + threadIdx.x;
     const double mu = sol[nhp];
     if (i < nxp) {
-        v[i] = A[(long)NP + (long)i * lda] - mu * A[(long)NP + 1 + (long)i * lda];
+        v[i] = A[(long)NP + (long)i * lda] - mu * A[(long)NP + 1 + (long)i * lda] - (wx ? wx[i] : 0.0);
     } else if (i < NP) {
         x[i] = sol[i - nxp];
     }
@@ -520,8 +627,27 @@ cudaError_t launch_set_identity_tiles(double* R, long ld, int nt, int row_begin,
 }
 
 cudaError_t launch_krylov_finish(const double* A, long lda, int NP, int nxp, const double* sol, int nhp, double* v,
-                                 double* x, ScfState* state, cudaStream_t stream) {
-    krylov_finish_kernel<<<(NP + 255) / 256, 256, 0, stream>>>(A, lda, NP, nxp, sol, nhp, v, x, state);
+                                 double* x, ScfState* state, const double* wx, cudaStream_t stream) {
+    krylov_finish_kernel<<<(NP + 255) / 256, 256, 0, stream>>>(A, lda, NP, nxp, sol, nhp, v, x, state, wx);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_p2p_allreduce(const double* src, double* out, int len, const P2PAllreduce& pa, unsigned* done_counter,
+                                 int* error, cudaStream_t stream) {
+    const int grid = (len + 255) / 256;
+    p2p_push_kernel<<<grid, 256, 0, stream>>>(src, len, pa, done_counter);
+    p2p_combine_kernel<<<grid, 256, 0, stream>>>(pa, len, out, error);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rect_matvec_t(const double* M, long ld, int nt_rows, int nt_cols, int row_begin, int row_end,
+                                 const double* x, double* part, double* out, cudaStream_t stream) {
+    if (nt_cols <= 0) return cudaSuccess;
+    if (row_end > row_begin) {
+        dim3 grid((row_end - row_begin + 7) / 8, nt_cols);
+        rect_matvec_t_kernel<<<grid, 256, 0, stream>>>(M, ld, nt_rows, row_begin, row_end, x, part);
+    }
+    rect_matvec_reduce_kernel<<<nt_cols, 512, 0, stream>>>(part, nt_rows, row_begin, row_end, out);
     return cudaGetLastError();
 }
 
