@@ -258,8 +258,9 @@ struct cheq_ctx {
     // sums of the tiled matrix-vector products, the small vectors of GMRES, device / pinned-host scalars
     DeviceBuffer kr_R, kr_Rf, kr_part, kr_vec, kr_sc, kr_wx, kx_local;
     unsigned kx_seq = 0;              // rounds of the peer-memory all-reduce so far (identical on every rank)
-    int krylov_p2p = -1;              // CHEQ_KRYLOV_P2P: 1 peer-memory all-reduce, 0 ncclAllReduce, -1 automatic (peer memory
-                                      // from 4 ranks on: measured 0.221 vs 0.216 s at 2 ranks, where NCCL's latency is low)
+    int krylov_p2p = 0;               // CHEQ_KRYLOV_P2P: 1 peer-memory all-reduce, 0 ncclAllReduce (default), -1 peer memory
+                                      // from 4 ranks on.  Measured S20k: 0.221 vs 0.216 s at 2 ranks, 0.1733 vs 0.1732 s at 8: the three
+                                      // all-reduces of a step are not what limits it, so NCCL stays the default)
     int krylov_f32 = 1;               // CHEQ_KRYLOV_F32=0: apply the frozen factor from the fp64 R
     KrylovScalars* h_ksc = nullptr;   // pinned
     int morton = 1;                   // CHEQ_MORTON=0: atoms of one element stay in input order (test knob: a

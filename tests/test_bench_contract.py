@@ -51,3 +51,37 @@ def test_multi_gpu_lines_are_strong_scaling_of_the_same_metric(name, gpus):
     assert d["n_gpus"] == gpus and d["scaling"] == "strong" and d["metric"] == one["metric"]
     assert d["config"]["workload"] == one["config"]["workload"]          # the SAME system, solved together
     assert d["value"] < one["value"]                                     # and faster than on one GPU
+
+
+# ---- round 2 lines ----------------------------------------------------------------------------------------------
+def test_round2_single_gpu_line_carries_parity_and_a_measured_cpu_arm():
+    d = _line("r2_bench_v2_f32R_trusted.json")
+    assert BASE_KEYS <= set(d), BASE_KEYS - set(d)
+    assert d["metric"] == "qeq_solve_time_n20k_sto_fp64" and d["n_gpus"] == 1 and d["scaling"] == "strong"
+    assert d["value"] < 0.45                        # <= 0.45 s on one B200
+    p = d["parity"]
+    assert p["ok"] and p["iterations"] == p["iterations_ref"] == 18
+    assert p["dq"] <= 1e-8 and p["dmu"] <= 1e-8 and p["max_delta_trace_diff"] <= 1e-9
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and "ONE complete CPU solve" in c["sample"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 20001 * 49      # xyz + chi + hardness + radius + n
+    m = d["roofline_matvec"]
+    assert m["bound"] == "hbm" and m["peak"] and 0 < m["frac"] < 1
+    assert "1" in d["config"]["scf_modes"].split()[0]        # stale-factor iterations really ran
+    one_r1 = _line("r1_bench_v3.json")
+    assert d["value"] < 0.5 * one_r1["value"]
+
+
+@pytest.mark.parametrize("name, gpus", [("r2_bench_dist2_v1.json", 2), ("r2_bench_dist8_v1.json", 8)])
+def test_round2_multi_gpu_lines_check_themselves_against_a_single_gpu_solve(name, gpus):
+    d = _line(name)
+    assert d["n_gpus"] == gpus and d["scaling"] == "strong"
+    chk = d["dist_check"]
+    assert chk["dq"] < 1e-10 and chk["dmu"] < 1e-10 and chk["iterations"][0] == chk["iterations"][1]
+    assert d["value"] < _line("r2_bench_v2_f32R_trusted.json")["value"]
+
+
+def test_round2_s100k_line_is_a_bench_py_line():
+    d = _line("r2_bench_s100k_8gpu_v1.json")
+    assert d["metric"] == "qeq_solve_time_n100k_sto_fp64" and d["n_gpus"] == 8 and "S100k" in d["config"]["workload"]
+    assert d["config"]["factor_tflops_overall"] / d["roofline"]["peak"] >= 0.5   # north_star: >= 50 % of FP64 peak
