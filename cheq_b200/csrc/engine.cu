@@ -256,7 +256,7 @@ struct cheq_ctx {
         lu_f, lu_piv, sgn, sgn_flags, xsol;
     // stale-factor SCF iterations (kernels_krylov.cu): explicit R = L_hh^-T S of the frozen hydrogen factor, partial
     // sums of the tiled matrix-vector products, the small vectors of GMRES, device / pinned-host scalars
-    DeviceBuffer kr_R, kr_Rf, kr_part, kr_vec, kr_sc, kr_wx, kx_local;
+    DeviceBuffer kr_R, kr_Rf, kr_S0t, kr_tb, kr_part, kr_vec, kr_sc, kr_wx, kx_local;
     unsigned kx_seq = 0;              // rounds of the peer-memory all-reduce so far (identical on every rank)
     int krylov_p2p = 0;               // CHEQ_KRYLOV_P2P: 1 peer-memory all-reduce, 0 ncclAllReduce (default), -1 peer memory
                                       // from 4 ranks on.  Measured S20k: 0.221 vs 0.216 s at 2 ranks, 0.1733 vs 0.1732 s at 8: the three
@@ -1266,7 +1266,10 @@ struct Krylov {
     int nhp = 0, nt = 0, len = 0;               // len = nhp + 1 entries per vector
     long vs = 0;                                // vector stride (doubles)
     double *R = nullptr, *partN = nullptr, *partT = nullptr;
-    float* Rf = nullptr;                        // single-precision copy of R used by the preconditioner (shifted base like R)
+    float* Rf = nullptr;                        // fp32, TILE-MAJOR copy of the stored tiles of R used by the preconditioner
+    double* S0t = nullptr;                      // tile-major copy of this rank's tile columns of S0 (lower triangle)
+    const long long *baseR = nullptr, *baseS = nullptr;   // device: first-tile offsets per tile column (tile_matvec_kernel)
+    bool s0t_ready = false;
     double *tc = nullptr, *t1 = nullptr, *ws = nullptr, *d_cur = nullptr, *d_prev = nullptr, *d_frozen = nullptr,
            *sol = nullptr, *r = nullptr, *z = nullptr, *tmp1 = nullptr, *tmp2 = nullptr, *w = nullptr, *V = nullptr;
     KrylovScalars* sc = nullptr;
@@ -1316,7 +1319,7 @@ int krylov_allreduce_n(cheq_ctx* ctx, const Krylov& K, double* v, int len) {
 }
 int krylov_allreduce(cheq_ctx* ctx, const Krylov& K, double* v) { return krylov_allreduce_n(ctx, K, v, K.len); }
 
-int krylov_alloc(cheq_ctx* ctx, Krylov& K, int nhp, bool dist) {
+int krylov_alloc(cheq_ctx* ctx, Krylov& K, int nhp, bool dist, const uint8_t* col_mask_host) {
     K.nhp = nhp;
     K.nt = nhp / kTile;
     K.len = nhp + 1;
@@ -1336,7 +1339,35 @@ int krylov_alloc(cheq_ctx* ctx, Krylov& K, int nhp, bool dist) {
     }
     const size_t r_rows = (size_t)std::max(1, K.rb - K.ra) * kTile;
     CU(ctx->kr_R.ensure(r_rows * nhp * 8));
-    if (ctx->krylov_f32) CU(ctx->kr_Rf.ensure(r_rows * nhp * 4));
+    // tile-major copies: offsets of the first stored tile of every tile column (R: rows [ra, rb) on/above the
+    // diagonal, fp32; S0: this rank's columns on/below the diagonal, fp64)
+    K.Rf = nullptr;
+    K.S0t = nullptr;
+    K.s0t_ready = false;
+    if (ctx->krylov_f32) {
+        std::vector<long long> base(2 * (size_t)K.nt, -1);
+        long long tr = 0, ts = 0;
+        for (int j = 0; j < K.nt; ++j) {
+            const int cnt_r = std::min(j, K.rb - 1) - K.ra + 1;
+            if (cnt_r > 0) {
+                base[j] = tr * (long long)kTile * kTile;
+                tr += cnt_r;
+            }
+            if (!col_mask_host || col_mask_host[j]) {
+                base[K.nt + j] = ts * (long long)kTile * kTile;
+                ts += K.nt - j;
+            }
+        }
+        CU(ctx->kr_Rf.ensure(std::max<size_t>(16, (size_t)tr * kTile * kTile * 4)));
+        CU(ctx->kr_S0t.ensure(std::max<size_t>(16, (size_t)ts * kTile * kTile * 8)));
+        CU(ctx->kr_tb.ensure(base.size() * sizeof(long long)));
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaMemcpy(ctx->kr_tb.p, base.data(), base.size() * sizeof(long long), cudaMemcpyHostToDevice));
+        K.Rf = ctx->kr_Rf.as<float>();
+        K.S0t = ctx->kr_S0t.as<double>();
+        K.baseR = ctx->kr_tb.as<long long>();
+        K.baseS = K.baseR + K.nt;
+    }
     CU(ctx->kr_part.ensure((size_t)2 * K.nt * K.nt * kTile * 8));
     const size_t nvec = 12 + Krylov::kMaxBasis + 1;
     CU(ctx->kr_vec.ensure(nvec * K.vs * 8));
@@ -1344,7 +1375,6 @@ int krylov_alloc(cheq_ctx* ctx, Krylov& K, int nhp, bool dist) {
     if (!ctx->h_ksc) CU(cudaMallocHost((void**)&ctx->h_ksc, sizeof(KrylovScalars)));
     // R is addressed with GLOBAL tile-row indices: the base is shifted up by the rows this rank does not hold
     K.R = ctx->kr_R.as<double>() - (long)K.ra * kTile;
-    K.Rf = ctx->krylov_f32 ? ctx->kr_Rf.as<float>() - (long)K.ra * kTile : nullptr;
     K.partN = ctx->kr_part.as<double>();
     K.partT = K.partN + (size_t)K.nt * K.nt * kTile;
     double* v = ctx->kr_vec.as<double>();
@@ -1366,6 +1396,7 @@ int krylov_apply_sinv(cheq_ctx* ctx, Krylov& K, const double* in, double* out) {
     TileMatvecArgs a{};
     a.M = K.Rf ? (const void*)K.Rf : (const void*)K.R;
     a.f32 = K.Rf ? 1 : 0;
+    a.col_base = K.Rf ? K.baseR : nullptr;
     a.ld = (long)(K.rb - K.ra) * kTile;
     a.nt = K.nt;
     a.upper = 1;
@@ -1408,7 +1439,8 @@ int krylov_apply_sinv(cheq_ctx* ctx, Krylov& K, const double* in, double* out) {
 int krylov_apply_K(cheq_ctx* ctx, Krylov& K, const double* v, double* out, int op) {
     cudaStream_t st = ctx->stream;
     TileMatvecArgs a{};
-    a.M = K.S0;
+    a.M = K.s0t_ready ? K.S0t : K.S0;
+    a.col_base = K.s0t_ready ? K.baseS : nullptr;
     a.ld = K.ld0;
     a.nt = K.nt;
     a.upper = 0;
@@ -1502,9 +1534,13 @@ int krylov_freeze(cheq_ctx* ctx, Dense& D, Krylov& K, int nxp, const double* d_o
     int rc = krylov_build_R(D, K, nxp, 0, K.nhp);
     if (rc) return rc;
     CU(cudaMemcpyAsync(K.d_frozen, d_of_factor, (size_t)K.nhp * 8, cudaMemcpyDeviceToDevice, st));
-    if (K.Rf)
-        LAUNCH(launch_convert_upper_tiles_f32(K.R + (long)K.ra * kTile, K.Rf + (long)K.ra * kTile,
-                                              (long)(K.rb - K.ra) * kTile, K.nt, K.ra, K.rb, st));
+    if (K.Rf) {
+        LAUNCH(launch_pack_tiles(K.R, (long)(K.rb - K.ra) * kTile, K.Rf, 1, K.baseR, K.nt, 1, K.ra, K.rb, nullptr, st));
+        if (!K.s0t_ready) {
+            LAUNCH(launch_pack_tiles(K.S0, K.ld0, K.S0t, 0, K.baseS, K.nt, 0, 0, K.nt, K.col_mask, st));
+            K.s0t_ready = true;
+        }
+    }
     rc = krylov_apply_sinv(ctx, K, K.t1, K.ws);
     if (rc) return rc;
     LAUNCH(launch_precond_den(K.t1, K.ws, K.sc, K.nhp, st));
@@ -2048,8 +2084,12 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
         // must take the same decision, and they do: same sizes, same device type, same allocations so far
         size_t free_b = 0, total_b = 0;
         CU(cudaMemGetInfo(&free_b, &total_b));
-        const size_t need = (size_t)L.nhp * L.nhp * (ctx->krylov_f32 ? 12 : 8) / (dist ? 2 : 1) + ((size_t)256 << 20);
-        const size_t have_r = ctx->kr_R.cap + ctx->kr_Rf.cap;
+        // fp64 R (the largest row chunk of a group: about half) + fp32 tile-major upper tiles of it + tile-major copy of
+        // this rank's part of the lower triangle of S0
+        const size_t nh2 = (size_t)L.nhp * L.nhp;
+        const size_t need = nh2 * 8 / (dist ? 2 : 1) + (ctx->krylov_f32 ? nh2 * 2 / (dist ? 2 : 1) + nh2 * 4 / (dist ? ctx->world : 1) : 0) +
+                            ((size_t)512 << 20);
+        const size_t have_r = ctx->kr_R.cap + ctx->kr_Rf.cap + ctx->kr_S0t.cap;
         if (need > free_b + have_r) kry = false;
         if (dist) {
             int* flag = ctx->ipc_stage.as<int>() + 32;
@@ -2063,7 +2103,7 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
         }
     }
     if (kry) {
-        rc = krylov_alloc(ctx, K, L.nhp, dist);
+        rc = krylov_alloc(ctx, K, L.nhp, dist, dist ? ctx->pplan.mask.data() + L.nxp / kTile : nullptr);
         if (rc) return rc;
         K.S0 = ctx->S0.as<double>();
         K.ld0 = ld0;
@@ -2821,6 +2861,8 @@ void cheq_ctx_destroy(cheq_ctx* ctx) {
     }
     ctx->kr_R.release();
     ctx->kr_Rf.release();
+    ctx->kr_S0t.release();
+    ctx->kr_tb.release();
     ctx->kr_wx.release();
     ctx->kx_local.release();
     ctx->kr_part.release();

@@ -201,6 +201,7 @@ struct TileMatvecArgs {
     double* partT;
     const uint8_t* col_mask;   // nullable: tile columns owned by this rank
     int row_begin, row_end;    // tile rows held by this rank (row_end == 0: all)
+    const long long* col_base; // nullable: tile-major storage, element offset of the first stored tile of each column
 };
 
 struct TileReduceArgs {
@@ -231,9 +232,9 @@ cudaError_t launch_p2p_allreduce(const double* src, double* out, int len, const 
                                  int* error, cudaStream_t stream);
 cudaError_t launch_tile_matvec(const TileMatvecArgs& a, bool do_n, bool do_t, cudaStream_t stream);
 cudaError_t launch_tile_matvec_reduce(const TileReduceArgs& a, cudaStream_t stream);
-// R and Rf point at the first LOCAL tile row (global tile row row_begin)
-cudaError_t launch_convert_upper_tiles_f32(const double* R, float* Rf, long ld, int nt, int row_begin, int row_end,
-                                           cudaStream_t stream);
+// column-major (src, ld; src at global tile row 0) -> tile-major dst (float if to_f32), stored tiles only
+cudaError_t launch_pack_tiles(const double* src, long ld, void* dst, int to_f32, const long long* col_base, int nt,
+                              int upper, int row_begin, int row_end, const uint8_t* col_mask, cudaStream_t stream);
 cudaError_t launch_multi_dot(const double* V, long stride, const double* w, int len, double* out, int m,
                              bool with_norm, cudaStream_t stream);
 cudaError_t launch_gs_update(const double* V, long stride, double* w, int len, const double* h, double* hsum, int m,

@@ -53,7 +53,14 @@ tile_matvec_kernel(TileMatvecArgs a) {
     const bool diag = (i == j);
     // T_ELEM = float: the preconditioner's R is kept in single precision (half the bytes; GMRES only needs a FIXED
     // linear operator close to K_s^-1, the residuals that decide convergence are formed with the fp64 S0)
-    const T_ELEM* T = (const T_ELEM*)a.M + (long)i * kTile + (long)j * kTile * a.ld + lane;
+    // tile-major storage (col_base != nullptr): the stored tiles of tile column j are consecutive 128 x 128 blocks
+    // starting at element col_base[j] (first stored tile row: j for a lower triangle, row_begin for an upper one), so a
+    // warp streams ONE contiguous 64 / 128 KB block instead of 128 segments a whole matrix column apart -- at 100k
+    // atoms the column stride is 534 KB and the column-major walk thrashes the TLB
+    const long tile_ld = a.col_base ? kTile : a.ld;
+    const T_ELEM* T = (const T_ELEM*)a.M +
+                      (a.col_base ? a.col_base[j] + (long)(i - (a.upper ? a.row_begin : j)) * (kTile * kTile)
+                                  : (long)i * kTile + (long)j * kTile * a.ld) + lane;
     double xt[4] = {0.0, 0.0, 0.0, 0.0};
     if (DO_T) {
 #pragma unroll
@@ -68,7 +75,7 @@ tile_matvec_kernel(TileMatvecArgs a) {
     double keepT = 0.0;
 #pragma unroll 4
     for (int c = 0; c < kTile; ++c) {
-        const T_ELEM* p = T + (long)c * a.ld;
+        const T_ELEM* p = T + (long)c * tile_ld;
         double t[4];
 #pragma unroll
         for (int m = 0; m < 4; ++m) t[m] = (double)__ldg(p + 32 * m);   // default caching: a 3,000-atom system's S0 and R live in L2
@@ -102,7 +109,7 @@ tile_matvec_kernel(TileMatvecArgs a) {
         }
     }
     if (DO_N) {
-        double* outN = a.partN + ((long)j * a.nt + i) * kTile;
+        double* outN = a.partN + ((long)i * a.nt + j) * kTile;   // [output block][tile column]: contiguous for the reducer
 #pragma unroll
         for (int m = 0; m < 4; ++m) outN[lane + 32 * m] = accN[m];
     }
@@ -251,7 +258,7 @@ tile_matvec_reduce_kernel(TileReduceArgs a) {
         const int j0 = a.upper ? b : 0, j1 = a.upper ? a.nt - 1 : b;
         for (int j = j0 + g; j <= j1; j += 4) {
             if (a.col_mask && !a.col_mask[j]) continue;
-            s += a.partN[((long)j * a.nt + b) * kTile + r];
+            s += a.partN[((long)b * a.nt + j) * kTile + r];
         }
     }
     if (a.partT) {
@@ -542,24 +549,36 @@ cudaError_t launch_tile_matvec(const TileMatvecArgs& a, bool do_n, bool do_t, cu
     return cudaGetLastError();
 }
 
-// upper tiles (i <= j) of the local rows of R: double -> float, same leading dimension (in elements)
+// Repack the stored tiles of a column-major matrix into tile-major order (see tile_matvec_kernel), optionally
+// converting to float.  src points at global tile row 0 (shifted base allowed); tile (i, j) goes to
+// dst + col_base[j] + (i - i0(j)) * 128 * 128, i0(j) = upper ? row_begin : j.
+template <class TOUT>
 __global__ void __launch_bounds__(256)
-convert_upper_tiles_f32_kernel(const double* R, float* Rf, long ld, int row_begin, int row_end) {
-    const int ti = row_begin + blockIdx.x, tj = blockIdx.y;
-    if (ti >= row_end || ti > tj) return;
-    const long off = (long)(ti - row_begin) * kTile + (long)tj * kTile * ld;
+pack_tiles_kernel(const double* src, long ld, TOUT* dst, const long long* col_base, int nt, int upper, int row_begin,
+                  int row_end, const uint8_t* col_mask) {
+    const int tj = blockIdx.y;
+    if (col_mask && !col_mask[tj]) return;
+    const int ti = (upper ? row_begin : tj) + blockIdx.x;
+    if (upper ? (ti > tj || ti >= row_end) : (ti >= nt)) return;
+    const double* s0 = src + (long)ti * kTile + (long)tj * kTile * ld;
+    TOUT* d0 = dst + col_base[tj] + (long)blockIdx.x * (kTile * kTile);
     for (int idx = threadIdx.x; idx < kTile * kTile / 2; idx += 256) {
         const int r2 = idx & 63, c = idx >> 6;
-        const double2 v = *(const double2*)(R + off + 2 * r2 + (long)c * ld);
-        *(float2*)(Rf + off + 2 * r2 + (long)c * ld) = make_float2((float)v.x, (float)v.y);
+        const double2 v = *(const double2*)(s0 + 2 * r2 + (long)c * ld);
+        d0[2 * r2 + c * kTile] = (TOUT)v.x;
+        d0[2 * r2 + 1 + c * kTile] = (TOUT)v.y;
     }
 }
 
-cudaError_t launch_convert_upper_tiles_f32(const double* R, float* Rf, long ld, int nt, int row_begin, int row_end,
-                                           cudaStream_t stream) {
-    if (row_end <= row_begin) return cudaSuccess;
-    dim3 grid(row_end - row_begin, nt);
-    convert_upper_tiles_f32_kernel<<<grid, 256, 0, stream>>>(R, Rf, ld, row_begin, row_end);
+cudaError_t launch_pack_tiles(const double* src, long ld, void* dst, int to_f32, const long long* col_base, int nt,
+                              int upper, int row_begin, int row_end, const uint8_t* col_mask, cudaStream_t stream) {
+    const int rows = upper ? (row_end - row_begin) : nt;
+    if (rows <= 0) return cudaSuccess;
+    dim3 grid(rows, nt);
+    if (to_f32)
+        pack_tiles_kernel<float><<<grid, 256, 0, stream>>>(src, ld, (float*)dst, col_base, nt, upper, row_begin, row_end, col_mask);
+    else
+        pack_tiles_kernel<double><<<grid, 256, 0, stream>>>(src, ld, (double*)dst, col_base, nt, upper, row_begin, row_end, col_mask);
     return cudaGetLastError();
 }
 

@@ -11,10 +11,6 @@ echo "rc=$?"; tail -8 $OUT/${TAG}_dist2_parity.txt | cut -c1-200
 echo "== bench --gpus 2"; date
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 2 --steps 3 --warmup 3 --no-secondary > $OUT/${TAG}_bench_dist2.json 2> $OUT/${TAG}_bench_dist2.err
 echo "rc=$?"; head -c 200 $OUT/${TAG}_bench_dist2.json; echo
-echo "== bench --gpus 2, NCCL all-reduce"; date
-CHEQ_KRYLOV_P2P=0 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node=2 --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus 2 --steps 3 --warmup 3 --no-secondary > $OUT/${TAG}_bench_dist2_nccl.json 2> $OUT/${TAG}_bench_dist2_nccl.err
-echo "rc=$?"; head -c 200 $OUT/${TAG}_bench_dist2_nccl.json; echo
-echo "== 1 GPU: W8k / policy tests + bench"; date
 timeout 900 python -m pytest tests/test_gpu_headline.py -m gpu -q -s --timeout 600 -k "w8k or policy" > $OUT/${TAG}_pytest.log 2>&1
 echo "rc=$?"; tail -3 $OUT/${TAG}_pytest.log
 timeout 600 python bench.py --steps 3 --warmup 3 --no-secondary --no-cpu-baseline > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
