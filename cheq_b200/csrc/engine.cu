@@ -268,7 +268,8 @@ struct cheq_ctx {
     int krylov_mode = 1;              // CHEQ_KRYLOV=0: refactor the hydrogen block in every SCF iteration
     int krylov_min_nhp = 4096;        // CHEQ_KRYLOV_MIN_NH: smallest padded hydrogen block that uses the stale factor (B3k,
                                       // nhp = 2048: 33.6 ms with it vs 23.7 ms without -- its GMRES steps are launch-latency-bound)
-    double krylov_freeze_ev = 4.5;    // CHEQ_KRYLOV_FREEZE_EV: freeze once max |D_k - D_(k-1)| falls below this
+    double krylov_freeze_ev = 0.0;    // CHEQ_KRYLOV_FREEZE_EV: freeze once max |D_k - D_(k-1)| falls below this many eV;
+                                      // 0 = from the cost model in factor_and_scf (3.5 .. 12 eV)
     int krylov_force_it = 5;          // ... or at this SCF iteration at the latest
     int matfree_restart = 160;        // CHEQ_MATFREE_RESTART: GMRES restart length of the matrix-free path
     int matfree_max_steps = 4000;     // CHEQ_MATFREE_MAX_STEPS: operator applications per SCF iteration
@@ -545,6 +546,13 @@ int upload_tables(cheq_ctx* ctx, const PackedTables& pk, PairTableView& dev_view
     return CHEQ_OK;
 }
 
+// |pivot| below this is treated as a breakdown of the unpivoted factorisation -> pivoted-LU path.  The test is
+// RELATIVE to the matrix scale: kPivotRel times the largest hardness of the system (the diagonal of the
+// matrix, 4..30 eV for the default table), so accepted pivots bound the element growth by ~1e5 (error ~1e-11) whatever
+// the units of the parameter set; kPivotTol is the absolute value used where no hardness is at hand (the test hooks).
+constexpr double kPivotTol = 1.0e-4;
+constexpr double kPivotRel = 1.0e-5;
+
 // ---- factorisation driver ------------------------------------------------------------------------------------
 struct Dense {
     cheq_ctx* ctx;
@@ -561,15 +569,13 @@ struct Dense {
     int* neg_idx;       // [batch][NP / 128][128] their in-tile indices
     long strideNeg;
     double flops = 0.0;
+    double pivot_tol = kPivotTol;             // absolute threshold for this solve (relative test resolved on the host)
     const struct SplitPlan* plan = nullptr;   // wave-aware recursion splits (nullptr: halve)
     bool push = false;                        // panel outputs are also stored into the peers' memory (epilogues)
     bool push_dma = false;                    // each finished tile column is copied to the peers by the copy engines
 };
 
 
-// |pivot| below this (eV) is treated as a breakdown of the unpivoted factorisation -> pivoted-LU path.
-// Matrix entries are O(1..30) eV, so accepted pivots bound the element growth by ~1e5 (error ~1e-11).
-constexpr double kPivotTol = 1.0e-4;
 
 int prof_begin(cheq_ctx* ctx, int category) {
     if (!ctx->profile) return CHEQ_OK;
@@ -637,7 +643,7 @@ int factor_panel(Dense& D, int j0, int n) {
             }
         }
         LAUNCH(launch_potrf_tile(Ajj, D.ld, D.strideA, Lk, D.strideLinv, D.sgn + j0, D.strideSgn, D.neg_cnt + j0 / kTile,
-                                 D.neg_idx + (long)j0, D.strideNeg, D.state, kPivotTol, D.batch, ctx->cur,
+                                 D.neg_idx + (long)j0, D.strideNeg, D.state, D.pivot_tol, D.batch, ctx->cur,
                                  D.push ? &pp : nullptr));
         if (int rcp = prof_end(ctx)) return rcp;
         const int mt = (D.MT - j0 - kTile) / kTile;
@@ -745,7 +751,7 @@ int factor_panel_flat(Dense& D, int j0, int n) {
             }
         }
         LAUNCH(launch_potrf_tile(Ajj, D.ld, D.strideA, Lk, D.strideLinv, D.sgn + jt, D.strideSgn, D.neg_cnt + jt / kTile,
-                                 D.neg_idx + (long)jt, D.strideNeg, D.state, kPivotTol, D.batch, ps,
+                                 D.neg_idx + (long)jt, D.strideNeg, D.state, D.pivot_tol, D.batch, ps,
                                  D.push ? &pp : nullptr));
         if (int rcp = prof_end(ctx)) return rcp;
         D.flops += tile3 / 3.0;
@@ -1743,6 +1749,7 @@ struct Prepared {
     double rcut2_max = INFINITY;
     long strideA = 0;
     int batch = 1;
+    double max_hardness = 0.0;   // scale of the matrix diagonal (host pointers only; 0: unknown)
 };
 
 // Which factorisation schedule a solve uses.  Right-looking panels with look-ahead are required for a group.  On
@@ -1838,6 +1845,8 @@ int prepare_and_assemble(cheq_ctx* ctx, const SolveIO& io, long frame0, int batc
     const Layout& L = P.L;
     P.batch = batch;
     P.strideA = (long)L.ld * L.NP;
+    if (!io.device_ptrs && P.max_hardness == 0.0)
+        for (long i = 0; i < n; ++i) P.max_hardness = std::max(P.max_hardness, std::fabs(io.hard[i]));
     ctx->stats.n_atoms = n;
     ctx->stats.n_hydrogen = L.scf ? L.nh : 0;
     ctx->stats.n_padded = L.NP;
@@ -1986,6 +1995,7 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
     Dense D{ctx, ctx->A.as<double>(), L.ld, P.strideA, ctx->Linv.as<double>(), (long)L.NP * kTile, L.MT,
             ctx->state.as<ScfState>(), batch, ctx->sgn.as<double>(), (long)L.NP, ctx->sgn_flags.as<int>(),
             ctx->sgn_flags.as<int>() + (size_t)(L.NP / kTile) * batch, (long)L.NP / kTile};
+    if (P.max_hardness > 0.0) D.pivot_tol = kPivotRel * P.max_hardness;
     double damping0 = 1.0;   // implementation.rs:297-301
     if (L.scf && o.damping_kind != CHEQ_DAMPING_NONE) damping0 = o.damping_value;
     LAUNCH(launch_scf_init(ctx->state.as<ScfState>(), damping0, batch, st));
@@ -2128,6 +2138,21 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
             if (rc) return rc;
         }
     }
+    // When to stop refactorising.  A refactorisation costs T_f; keeping a factor whose shift is d eV away costs about
+    // 1.4 d extra GMRES steps in each of the ~14 iterations that follow (measured: 36 / 20 / 13 / 9 / 7 steps at
+    // d = 8 / 6 / 3.4 / 0.8 / 0.2 eV on S20k), and a refactorisation roughly halves d.  So refactor while
+    // d > T_f / (14 * 1.4 * T_step).  T_f and T_step come from a size model (identical on every rank of a group, which
+    // must take the same decision), calibrated on S20k (1 and 8 GPUs) and S100k (8 GPUs): S20k -> 3.5..4 eV (freeze at
+    // iteration 4, as tuned by hand), S100k on 8 GPUs -> 12 eV (freeze at iteration 2: a refactorisation there costs
+    // 525 ms, a GMRES step 1.6 ms).
+    double freeze_ev = ctx->krylov_freeze_ev;
+    if (kry && !(freeze_ev > 0.0)) {
+        const double w = dist ? ctx->world : 1;
+        const double nh = (double)L.nhp, tiles = nh / kTile;
+        const double t_f = nh * nh * nh / 3.0 / ((dist ? 22e12 : 25e12) * w) * 1e3 + tiles * (dist ? 0.17 : 0.075);
+        const double t_step = 8.0 * nh * nh / (4e12 * w) * 1e3 + (dist ? 0.4 : 0.15);
+        freeze_ev = std::min(12.0, std::max(3.5, t_f / (14.0 * 1.4 * t_step)));
+    }
     cudaEvent_t evk0 = ctx->ev[5], evk1 = ctx->ev[6];
     float krylov_ms = 0.0f;
     bool have_factor = false;        // the trapezoid's hydrogen block holds the factor for the shift in K.d_prev
@@ -2148,7 +2173,7 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
                 CU(cudaStreamSynchronize(st));
                 double dmax;
                 std::memcpy(&dmax, &ctx->h_ksc->dmax_bits, 8);
-                if (dmax <= ctx->krylov_freeze_ev || (int)it >= ctx->krylov_force_it) {
+                if (dmax <= freeze_ev || (int)it >= ctx->krylov_force_it) {
                     // the factor of the previous iteration becomes the preconditioner of all that follow
                     CU(cudaEventRecord(evk0, st));
                     D.flops = 0.0;
@@ -2928,6 +2953,7 @@ int32_t cheq_set_krylov(cheq_ctx* ctx, int32_t enabled, int32_t min_hydrogen, do
     if (enabled >= 0) ctx->krylov_mode = enabled != 0;
     if (min_hydrogen > 0) ctx->krylov_min_nhp = std::max(128, (int)min_hydrogen);
     if (freeze_ev > 0.0) ctx->krylov_freeze_ev = freeze_ev;
+    else if (freeze_ev < 0.0) ctx->krylov_freeze_ev = 0.0;   // back to the cost model
     if (force_iteration > 0) ctx->krylov_force_it = std::max(2, (int)force_iteration);
     return CHEQ_OK;
 }

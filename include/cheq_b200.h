@@ -120,7 +120,9 @@ int32_t cheq_get_scf_trace(const cheq_ctx* ctx, uint32_t capacity, double* delta
 /* Stale-factor policy.  enabled = 0 refactors the hydrogen block in every iteration (the
  * round-1 behaviour); min_hydrogen: smallest hydrogen block that uses the frozen factor; freeze_ev: freeze once the
  * largest change of the hydrogen diagonal between two iterations falls below this many eV; force_iteration: freeze at
- * this SCF iteration at the latest.  Negative / zero values keep the current setting. */
+ * this SCF iteration at the latest.  enabled < 0, min_hydrogen <= 0, freeze_ev == 0 and force_iteration <= 0 keep the
+ * current setting; freeze_ev < 0 selects the built-in cost model (the default: 3.5 .. 12 eV depending on the size of the
+ * hydrogen block and the number of GPUs). */
 int32_t cheq_set_krylov(cheq_ctx* ctx, int32_t enabled, int32_t min_hydrogen, double freeze_ev, int32_t force_iteration);
 
 /* ---- multi-GPU: one dense system across the GPUs of a node ----------------------------

@@ -125,7 +125,7 @@ def main():
     run_case("water750/GTO/scf/stale-factor", Z, xyz, SolverOptions(basis_type=BasisType.Gto), tpp=1)
     run_case(f"water{3 * big}/stale-factor", Zb, xb, SolverOptions(), oracle_check=False)
     assert ctx.stats()["krylov_iterations"] > 0
-    ctx.set_krylov(True, 4096, 4.5, 5)
+    ctx.set_krylov(True, 4096, -1.0, 5)
     # matrix-free path on the group: rows of the operator sharded, one all-gather per application
     chi, hard, rad, nq = workloads.gather_parameters(Z, P)
     s_it = QEqSolver(P, SolverOptions(), ctx)

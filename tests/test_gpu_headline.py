@@ -141,7 +141,7 @@ def test_stale_factor_policy_variants_b3k(gpu_ctx, oracle):
     ref = oracle.solve(Z, xyz, 0.0)
     for label, kw in (("freeze at 2", dict(freeze_ev=1e9, force_iteration=2)),
                       ("freeze when settled", dict(freeze_ev=0.5, force_iteration=9)),
-                      ("default", dict(freeze_ev=4.5, force_iteration=5))):
+                      ("hand-tuned round-2 value", dict(freeze_ev=4.5, force_iteration=5))):
         ctx = cheq_b200.Context(0)
         ctx.set_krylov(True, 128, kw["freeze_ev"], kw["force_iteration"])
         res, trace, st = solve_arrays(ctx, Z, xyz)
