@@ -14,7 +14,7 @@ from pathlib import Path
 PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "lib" / "libcheq_b200.so"
-SOURCES = ["engine.cu", "kernels_assemble.cu", "kernels_dense.cu", "kernels_krylov.cu", "kernels_lu.cu", "sto_tables.cpp"]
+SOURCES = ["engine.cu", "kernels_assemble.cu", "kernels_dense.cu", "kernels_krylov.cu", "kernels_lu.cu", "kernels_ozaki.cu", "sto_tables.cpp"]
 HEADERS = ["device_types.h", "kernels.h", "sto_tables.h", "../../include/cheq_b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-ldl",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-shared", "-cudart", "static"]

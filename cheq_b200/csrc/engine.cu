@@ -271,6 +271,15 @@ struct cheq_ctx {
     double krylov_freeze_ev = 0.0;    // CHEQ_KRYLOV_FREEZE_EV: freeze once max |D_k - D_(k-1)| falls below this many eV;
                                       // 0 = from the cost model in factor_and_scf (3.5 .. 12 eV)
     int krylov_force_it = 5;          // ... or at this SCF iteration at the latest
+    // FP64-equivalent updates on the tcgen05 tensor cores (kernels_ozaki.cu): int8 slices per operand, 0 = DMMA only
+    int ozaki_slices = 0;             // CHEQ_OZAKI: 4..8 (7 = 54 bits per entry relative to its row maximum: fp64 grade)
+    int ozaki_slices_r = 0;           // CHEQ_OZAKI_R: slices while building the frozen factor's R (a preconditioner, kept in
+                                      // fp32 afterwards); 0 = as CHEQ_OZAKI
+    int ozaki_min_k = 1024;           // CHEQ_OZAKI_MIN_K: shallower updates stay on DMMA (slicing + epilogue do not amortise)
+    int ozaki_now = 0;                // slices in force for the launches being issued
+    DeviceBuffer oz_ws, oz_err;
+    int* h_oz_err = nullptr;          // pinned
+    uint64_t oz_launches = 0;
     int matfree_restart = 160;        // CHEQ_MATFREE_RESTART: GMRES restart length of the matrix-free path
     int matfree_max_steps = 4000;     // CHEQ_MATFREE_MAX_STEPS: operator applications per SCF iteration
     double matfree_tol = 1e-12;       // CHEQ_MATFREE_TOL: |P (b - K x)| <= tol |x|
@@ -599,7 +608,32 @@ int prof_end(cheq_ctx* ctx) {
 int launch_gemm_timed(cheq_ctx* ctx, const GemmArgs& g, int mt, int nt, int batch, double flops) {
     int rc = prof_begin(ctx, 0);
     if (rc) return rc;
-    LAUNCH(launch_gemm_nt(g, mt, nt, batch, ctx->cur));
+    // deep single-frame updates go to the tcgen05 tensor cores as int8 slice products (kernels_ozaki.cu)
+    const int S = ctx->ozaki_now;
+    if (S > 0 && batch == 1 && g.subtract && !g.n_list && g.n_peers == 0 && g.K >= ctx->ozaki_min_k &&
+        ctx->cur == ctx->stream && ozaki_supported(S, std::min(g.K, kOzakiMaxK))) {
+        // K is cut into chunks whose int32 group sums cannot overflow; each chunk has its own row scales
+        for (int k0 = 0; k0 < g.K; k0 += kOzakiMaxK) {
+            GemmArgs c = g;
+            c.K = std::min(kOzakiMaxK, g.K - k0);
+            c.A = g.A + (long)k0 * g.lda;
+            c.B = g.B + (long)k0 * g.ldb;
+            if (g.neg_cnt) {
+                c.neg_cnt = g.neg_cnt + k0 / kTile;
+                c.neg_idx = g.neg_idx + k0;
+            }
+            const size_t need = ozaki_workspace_bytes(S, mt, nt, c.K);
+            if (need > ctx->oz_ws.cap) {
+                CU(cudaStreamSynchronize(ctx->cur));   // earlier launches may still read the old workspace
+                CU(ctx->oz_ws.ensure(need));
+            }
+            LAUNCH(launch_gemm_ozaki(c, mt, nt, S, ctx->oz_ws.p, ctx->oz_ws.cap, ctx->oz_err.as<int>(), ctx->cur));
+            ctx->launches += 4;   // two row-maximum and two slicing kernels ride along
+            ctx->oz_launches++;
+        }
+    } else {
+        LAUNCH(launch_gemm_nt(g, mt, nt, batch, ctx->cur));
+    }
     if (ctx->profile) {
         ctx->prof_flops += flops * batch;
         if (ctx->prof_shape.size() < ctx->prof_cat.size()) ctx->prof_shape.resize(ctx->prof_cat.size());
@@ -1537,7 +1571,9 @@ int krylov_build_R(Dense& D, Krylov& K, int h0, int j0, int n) {
 int krylov_freeze(cheq_ctx* ctx, Dense& D, Krylov& K, int nxp, const double* d_of_factor) {
     cudaStream_t st = ctx->stream;
     LAUNCH(launch_set_identity_tiles(K.R + (long)K.ra * kTile, (long)(K.rb - K.ra) * kTile, K.nt, K.ra, K.rb, st));
+    if (ctx->ozaki_slices_r) ctx->ozaki_now = ctx->ozaki_slices_r;
     int rc = krylov_build_R(D, K, nxp, 0, K.nhp);
+    ctx->ozaki_now = ctx->ozaki_slices;
     if (rc) return rc;
     CU(cudaMemcpyAsync(K.d_frozen, d_of_factor, (size_t)K.nhp * 8, cudaMemcpyDeviceToDevice, st));
     if (K.Rf) {
@@ -2281,7 +2317,13 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
             CU(cudaMemcpyAsync(ctx->h_active, ctx->active.p, sizeof(int), cudaMemcpyDeviceToHost, st));
             if (batch == 1) CU(cudaMemcpyAsync(ctx->h_state, ctx->state.p, sizeof(ScfState), cudaMemcpyDeviceToHost, st));
         }
+        if (ctx->h_oz_err) CU(cudaMemcpyAsync(ctx->h_oz_err, ctx->oz_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
+        if (ctx->h_oz_err && *ctx->h_oz_err) {
+            const int code = *ctx->h_oz_err;
+            cudaMemsetAsync(ctx->oz_err.p, 0, sizeof(int), st);
+            return fail(ctx, CHEQ_ERR_CUDA, "tcgen05 slice-product pipeline timed out (role " + std::to_string(code) + ")");
+        }
         if (batch == 1) ctx->trace.push_back({ctx->h_state[0].delta, use_krylov ? 1 : 0, gm_steps});
         if (*ctx->h_active == 0) break;
     }
@@ -2828,6 +2870,22 @@ int32_t cheq_ctx_create(int32_t device, cheq_ctx** out) {
         cheq_ctx_destroy(ctx);
         return CHEQ_ERR_CUDA;
     }
+    if (const char* env = getenv("CHEQ_OZAKI")) ctx->ozaki_slices = atoi(env);
+    if (const char* env = getenv("CHEQ_OZAKI_R")) ctx->ozaki_slices_r = atoi(env);
+    if (const char* env = getenv("CHEQ_OZAKI_MIN_K")) ctx->ozaki_min_k = std::max(128, atoi(env));
+    if (ctx->ozaki_slices != 0 && (ctx->ozaki_slices < 4 || ctx->ozaki_slices > 8)) ctx->ozaki_slices = 7;
+    if (ctx->ozaki_slices_r != 0 && (ctx->ozaki_slices_r < 4 || ctx->ozaki_slices_r > 8)) ctx->ozaki_slices_r = 0;
+    if (ctx->ozaki_slices || ctx->ozaki_slices_r) {
+        if (configure_ozaki_kernels() != cudaSuccess || ctx->oz_err.ensure(64) != cudaSuccess ||
+            cudaMemset(ctx->oz_err.p, 0, 64) != cudaSuccess ||
+            cudaMallocHost((void**)&ctx->h_oz_err, sizeof(int)) != cudaSuccess) {
+            cudaGetLastError();
+            cheq_ctx_destroy(ctx);
+            return CHEQ_ERR_CUDA;
+        }
+        *ctx->h_oz_err = 0;
+    }
+    ctx->ozaki_now = ctx->ozaki_slices;
     if (const char* env = getenv("CHEQ_MORTON")) ctx->morton = atoi(env) != 0;
     if (const char* env = getenv("CHEQ_MATFREE_RESTART")) ctx->matfree_restart = atoi(env);
     if (const char* env = getenv("CHEQ_MATFREE_MAX_STEPS")) ctx->matfree_max_steps = std::max(10, atoi(env));
@@ -2896,6 +2954,9 @@ void cheq_ctx_destroy(cheq_ctx* ctx) {
     if (ctx->h_ksc) cudaFreeHost(ctx->h_ksc);
     if (ctx->h_state) cudaFreeHost(ctx->h_state);
     if (ctx->h_active) cudaFreeHost(ctx->h_active);
+    if (ctx->h_oz_err) cudaFreeHost(ctx->h_oz_err);
+    ctx->oz_ws.release();
+    ctx->oz_err.release();
     for (auto& e : ctx->ev)
         if (e) cudaEventDestroy(e);
     for (auto& e : ctx->prof_events)

@@ -124,6 +124,17 @@ cudaError_t launch_block_jacobi_apply(const double* Minv, const double* sgn, con
 
 // ---- dense (kernels_dense.cu) ------------------------------------------------------------------------------
 cudaError_t launch_gemm_nt(const GemmArgs& g, int m_tiles, int n_tiles, int batch, cudaStream_t stream);
+// ---- FP64-equivalent GEMM on the tcgen05 tensor cores (kernels_ozaki.cu) ------------------------------------------
+// C -= A S B^T with both operands split into `slices` int8 planes per entry (row-scaled, error-free), the slice
+// products on tcgen05.mma.kind::i8 with int32 accumulators in TMEM, recombined in fp64.  Single frame, no column
+// list, no peers; K a multiple of 128 and at most kOzakiMaxK (int32 group sums); `error`: device flag raised if the
+// copy / MMA pipeline times out (C is then left untouched by the remaining CTAs).
+constexpr int kOzakiMaxK = 8192;
+size_t ozaki_workspace_bytes(int slices, int m_tiles, int n_tiles, int K);
+bool ozaki_supported(int slices, int K);
+cudaError_t configure_ozaki_kernels();
+cudaError_t launch_gemm_ozaki(const GemmArgs& g, int m_tiles, int n_tiles, int slices, void* ws, size_t ws_bytes,
+                              int* error, cudaStream_t stream);
 cudaError_t launch_dmma_rate(double* out, int blocks, int threads, int iters, cudaStream_t stream);
 cudaError_t launch_latency_probe(double* out, long long* cycles, int iters, cudaStream_t stream);
 cudaError_t launch_dfma_rate(double* out, int blocks, int iters, cudaStream_t stream);
