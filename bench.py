@@ -346,6 +346,23 @@ def hbm_peak_gbs():
         return None
 
 
+def int8_peak_tops():
+    """Dense int8 tensor peak for the tcgen05 slice-product kernel, in 10^12 operations per second.  MEASURED_PEAKS.json
+    holds the bf16 figure; int8 runs at twice that rate nominally.  The larger of that and the int8 issue rate this
+    repository measured itself (tools/tc05_probe: back-to-back M128 N256 K32 tcgen05.mma.kind::i8 on every SM) is used, so
+    the fraction is never flattered."""
+    probe = (profile_record("int8_issue_rate") or {}).get("tops")
+    try:
+        bf16 = float(json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["bf16_tflops"])
+        src = f"2 x MEASURED_PEAKS.json bf16_tflops (burst) = {2 * bf16:.0f}"
+    except Exception:
+        bf16, src = 1590.0, "2 x 1590 (fallback bf16 figure of B200_PROFILING.md)"
+    peak = 2.0 * bf16
+    if probe and probe > peak:
+        peak, src = float(probe), src + f"; the measured tcgen05 int8 issue rate {probe:.0f} is higher and is used (profiles/r2_tcgen05_int8_probe.json)"
+    return peak, src
+
+
 def profile_record(key):
     """Facts that only an ncu capture can give (DRAM traffic, pipe utilisation) live in profiles/r2_ncu_facts.json,
     written from the committed ncu summaries -- never typed into this file."""
@@ -593,8 +610,8 @@ def run_ours(args, rank, local_rank, world):
     # pass 2: the same K steps with every launch of the dominant kernel bracketed by CUDA events on the engine's
     # stream (two event records per launch cost a few % of the step, hence not in pass 1)
     lib.cheq_set_profiling(ctx.handle, 1)
-    gemm_ms = gemm_fl = 0.0
-    gemm_n = 0
+    gemm_ms = gemm_fl = tc_ms = tc_fl = tc_ops = 0.0
+    gemm_n = tc_n = 0
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record(stream)
     for _ in range(args.steps):
@@ -603,6 +620,10 @@ def run_ours(args, rank, local_rank, world):
         gemm_ms += st["gemm_ms"]
         gemm_fl += st["gemm_flops"]
         gemm_n += st["gemm_launches"]
+        tc_ms += st["tc_gemm_ms"]
+        tc_fl += st["tc_gemm_flops"]
+        tc_ops += st["tc_gemm_ops"]
+        tc_n += st["tc_gemm_launches"]
     e3.record(stream)
     torch.cuda.synchronize()
     ms_profiled = e2.elapsed_time(e3)
@@ -616,6 +637,7 @@ def run_ours(args, rank, local_rank, world):
     for _ in range(min(args.warmup, 1)):
         step_host()
     ms_e2e = timed(step_host, args.steps)
+    stats_e2e = ctx.stats()
     assert abs(pot.value - mu_dev) < 1e-9 and np.max(np.abs(h_q.numpy() - q_dev)) < 1e-9
 
     secondary = None
@@ -634,7 +656,32 @@ def run_ours(args, rank, local_rank, world):
     value = ms_per_step / 1e3
     e2e_value = ms_e2e / args.steps / 1e3
     peak_burst, peak_sustained = measure_fp64_peak(torch, device)
-    achieved = gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    # the updates split into two kernels: deep ones as int8 slice products on tcgen05 (oz_gemm_kernel), the rest on DMMA
+    dmma_ms, dmma_fl, dmma_n = gemm_ms - tc_ms, gemm_fl - tc_fl, gemm_n - tc_n
+    achieved = dmma_fl / (dmma_ms * 1e-3) / 1e12 if dmma_ms > 0 else 0.0
+    dmma_block = {"bound": "tensor", "kernel": "gemm_nt_kernel (FP64 DMMA.8x8x4)", "achieved": achieved,
+                  "peak": peak_sustained, "unit": "TFLOP/s", "frac": achieved / peak_sustained if peak_sustained else None,
+                  "traffic": None, "launches": dmma_n, "kernel_ms_per_step": dmma_ms / args.steps,
+                  "share_of_step": dmma_ms / ms_profiled,
+                  "largest_launch": profile_record("gemm_largest_launch") if (n == 20001 and tc_n == 0) else None,
+                  "peak_source": f"cuBLAS DGEMM 8192^3 measured in this run: sustained {peak_sustained:.1f}, "
+                                 f"burst {peak_burst:.1f} TFLOP/s (MEASURED_PEAKS.json has no fp64 entry)"}
+    tc_block = None
+    if tc_n > 0:
+        int8_peak, int8_src = int8_peak_tops()
+        tc_tops = tc_ops / (tc_ms * 1e-3) / 1e12
+        tc_block = {"bound": "tensor",
+                    "kernel": "oz_gemm_kernel (tcgen05.mma.kind::i8 slice products with TMEM accumulators: the FP64-equivalent "
+                              "updates C -= A S B^T), timed together with its slicing passes",
+                    "achieved": tc_tops, "peak": int8_peak, "unit": "TFLOP/s", "frac": tc_tops / int8_peak,
+                    "achieved_is": "int8 tensor operations per second (2 x multiply-adds, in 10^12/s): algorithmic FP64 "
+                                   "flops x slice products per entry (28 at 7 slices, 15 at 5)",
+                    "fp64_equivalent_tflops": tc_fl / (tc_ms * 1e-3) / 1e12,
+                    "fp64_equivalent_vs_dgemm_peak": tc_fl / (tc_ms * 1e-3) / 1e12 / peak_sustained if peak_sustained else None,
+                    "traffic": (profile_record("oz_largest_launch") or {}).get("traffic") if n == 20001 else None,
+                    "launches": tc_n, "kernel_ms_per_step": tc_ms / args.steps, "share_of_step": tc_ms / ms_profiled,
+                    "largest_launch": profile_record("oz_largest_launch") if n == 20001 else None,
+                    "peak_source": int8_src}
     hbm_peak = hbm_peak_gbs()
     asm_gbs = stats["bytes_assemble"] / (stats["ms_assemble"] * 1e-3) / 1e9 if stats["ms_assemble"] > 0 else 0.0
     asm_gbs_per_gpu = asm_gbs / world          # every rank assembles 1/world of the tile columns in that time
@@ -678,20 +725,17 @@ def run_ours(args, rank, local_rank, world):
                    "krylov_ms": stats_plain["krylov_ms"],
                    "factor_tflops_overall": stats_plain["flops_factor"] / ((stats_plain["ms_factor_once"] + stats_plain["ms_scf"]) * 1e9),
                    "lu_fallback_frames": stats_plain["lu_fallback_frames"]},
-        "roofline": {"bound": "tensor", "kernel": "gemm_nt_kernel (FP64 DMMA.8x8x4)", "achieved": achieved,
-                     "peak": peak_sustained, "unit": "TFLOP/s", "frac": achieved / peak_sustained if peak_sustained else None,
-                     "traffic": None, "launches": gemm_n, "kernel_ms_per_step": gemm_ms / args.steps,
-                     "largest_launch": profile_record("gemm_largest_launch") if n == 20001 else None,
-                     "share_of_step": gemm_ms / ms_profiled,
-                     "measured_in": f"second pass of {args.steps} steps with per-launch CUDA events "
-                                    f"({ms_profiled / args.steps:.1f} ms per step vs {ms_total / args.steps:.1f} uninstrumented)",
-                     "potrf_ms_per_step": stats["potrf_ms"], "backsolve_ms_per_step": stats["backsolve_ms"],
-                     "note": ("panel schedule: GEMMs of the main, panel and bulk streams run concurrently, so the "
-                              "summed per-launch durations overstate the kernel's wall-clock share and understate "
-                              "its rate" if (world > 1 or os.environ.get("CHEQ_FACTOR_MODE") == "1") else
-                              "recursive schedule: one stream, launches do not overlap"),
-                     "peak_source": f"cuBLAS DGEMM 8192^3 measured in this run: sustained {peak_sustained:.1f}, "
-                                    f"burst {peak_burst:.1f} TFLOP/s (MEASURED_PEAKS.json has no fp64 entry)"},
+        # the dominant kernel by time: the tcgen05 slice-product kernel when it ran and took longer than the DMMA one
+        "roofline": dict(tc_block if (tc_block and tc_ms >= dmma_ms) else dmma_block,
+                         measured_in=f"second pass of {args.steps} steps with per-launch CUDA events "
+                                     f"({ms_profiled / args.steps:.1f} ms per step vs {ms_total / args.steps:.1f} uninstrumented)",
+                         potrf_ms_per_step=stats["potrf_ms"], backsolve_ms_per_step=stats["backsolve_ms"],
+                         all_updates_fp64_tflops=gemm_fl / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else None,
+                         note=("panel schedule: GEMMs of the main, panel and bulk streams run concurrently, so the "
+                               "summed per-launch durations overstate the kernel's wall-clock share and understate "
+                               "its rate" if (world > 1 or os.environ.get("CHEQ_FACTOR_MODE") == "1") else
+                               "recursive schedule: one stream, launches do not overlap")),
+        "roofline_other_gemm": (dmma_block if (tc_block and tc_ms >= dmma_ms) else tc_block),
         "roofline_matvec": {"bound": "hbm", "kernel": "tile_matvec_kernel (stale-factor SCF iterations: one pass over "
                                                       "the lower triangle of S0 + two over the upper triangle of R per step)",
                             "achieved": kry_gbs, "peak": hbm_peak, "unit": "GB/s",
@@ -706,7 +750,9 @@ def run_ours(args, rank, local_rank, world):
                               "note": "per GPU: algorithmic bytes 8 N (N + 1) / 2 / n_gpus over the assembly time",
                               "peak_source": "MEASURED_PEAKS.json hbm_gbs"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * (24 + 8 + 8 + 8 + 1)),
-                "d2h_bytes_per_step": int(n * 8 + 64)},
+                "d2h_bytes_per_step": int(n * 8 + 64),
+                "phases_ms_last_step": {k: stats_e2e[k] for k in ("ms_total", "ms_host_prepare", "ms_h2d", "ms_assemble",
+                                                                  "ms_factor_once", "ms_scf", "ms_d2h")}},
         "gpu_launches": int(launches_t.item()),
         "clocks": clocks,
         "parity": parity,

@@ -33,7 +33,9 @@ class Stats(C.Structure):
                 ("lu_fallback_frames", C.c_uint64), ("gemm_ms", C.c_double), ("gemm_flops", C.c_double),
                 ("gemm_launches", C.c_uint64), ("potrf_ms", C.c_double), ("backsolve_ms", C.c_double),
                 ("krylov_iterations", C.c_uint64), ("krylov_steps", C.c_uint64), ("krylov_ms", C.c_double),
-                ("krylov_bytes", C.c_double), ("matfree_matvecs", C.c_uint64), ("matfree_pairs", C.c_double)]
+                ("krylov_bytes", C.c_double), ("matfree_matvecs", C.c_uint64), ("matfree_pairs", C.c_double),
+                ("tc_gemm_launches", C.c_uint64), ("tc_gemm_flops", C.c_double), ("tc_gemm_ops", C.c_double),
+                ("tc_gemm_ms", C.c_double)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -51,6 +53,7 @@ SIGNATURES = {
     "cheq_set_profiling": (_I32, [_P, _I32]),
     "cheq_get_scf_trace": (_I32, [_P, C.c_uint32, _P, _P, _P, C.POINTER(C.c_uint32)]),
     "cheq_set_krylov": (_I32, [_P, _I32, _I32, _D, _I32]),
+    "cheq_set_ozaki": (_I32, [_P, _I32, _I32, _I32]),
     "cheq_dist_unique_id": (_I32, [_P]),
     "cheq_ctx_dist_init": (_I32, [_P, _I32, _I32, _P]),
     "cheq_ctx_dist_info": (_I32, [_P, C.POINTER(_I32), C.POINTER(_I32)]),
@@ -68,6 +71,7 @@ SIGNATURES = {
     "cheq_external_potential": (_I32, [_P, _U64, _P, _P, _P, C.POINTER(External), _D, _U8, _P]),
     "cheq_dbg_cholesky_solve": (_I32, [_P, _U64, _P, _U64, _P, _P, _P]),
     "cheq_dbg_gemm_nt": (_I32, [_P, _U64, _U64, _U64, _P, _P, _P, _I32]),
+    "cheq_dbg_gemm_ozaki": (_I32, [_P, _U64, _U64, _U64, _P, _P, _P, _I32, _I32, _I32, _P]),
     "cheq_dbg_potrf_cycles": (_I32, [_P, _P, _I32]),
     "cheq_dbg_dfma_rate": (_I32, [_P, C.POINTER(_D)]),
     "cheq_dbg_gemm_bench": (_I32, [_P, _U64, _U64, _U64, _I32, _I32, _I32, C.POINTER(_D)]),

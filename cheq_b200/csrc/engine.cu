@@ -103,7 +103,18 @@ struct SplitPlan {
     int nmax = 0;
     std::vector<short> split;   // [j0t * (nmax + 1) + n] = tiles in the left part
     std::vector<float> cost;
-    static double gemm_cost(long mt, long nt, long k_tiles, bool lower, int batch) {
+    int oz_slices = 0, oz_min_k = 0;   // > 0: single-frame updates at least this deep run as int8 slice products
+    // tcgen05 path (kernels_ozaki.cu), microseconds, from tools/ozaki_probe on B200: 128 x 64 tiles in waves of 148,
+    // 2.6 us per 128-deep K tile at 7 slices (28 slice products) + ~4 us of prologue / epilogue per CTA, plus the
+    // slicing passes (0.13 us per 128 x 128 block of an operand and five short launches)
+    static double gemm_cost_oz(long mt, long nt, long k_tiles, bool lower, int S) {
+        const long tiles = lower ? nt * (nt + 1) / 2 + (mt - nt) * nt : mt * nt;
+        if (tiles <= 0) return 0.0;
+        const double per_k = 2.6 * (S * (S + 1) / 2.0) / 28.0;
+        return std::ceil(2.0 * tiles / 148.0) * (k_tiles * per_k + 4.0) + (double)(mt + nt) * k_tiles * 0.13 + 12.0;
+    }
+    double gemm_cost(long mt, long nt, long k_tiles, bool lower, int batch) const {
+        if (oz_slices > 0 && batch == 1 && k_tiles * kTile >= oz_min_k) return gemm_cost_oz(mt, nt, k_tiles, lower, oz_slices);
         long tiles = lower ? nt * (nt + 1) / 2 + (mt - nt) * nt : mt * nt;
         if (tiles <= 0) return 0.0;
         tiles *= batch;
@@ -111,10 +122,12 @@ struct SplitPlan {
         if (tiles <= 74) return std::ceil(2.0 * tiles / 148.0) * (ktiles16 * 1.25 + 8.0);
         return std::ceil(tiles / 148.0) * (ktiles16 * 2.44 + 9.5);
     }
-    void build(int mt_total_, int j_begin, int j_end, int batch_) {
+    void build(int mt_total_, int j_begin, int j_end, int batch_, int oz_slices_ = 0, int oz_min_k_ = 0) {
         // plan for panels inside tile columns [j_begin, j_end)
         mt_total = mt_total_;
         batch = batch_;
+        oz_slices = oz_slices_;
+        oz_min_k = oz_min_k_;
         nmax = j_end;
         split.assign((size_t)(nmax + 1) * (nmax + 1), 0);
         cost.assign((size_t)(nmax + 1) * (nmax + 1), 0.0f);
@@ -272,14 +285,15 @@ struct cheq_ctx {
                                       // 0 = from the cost model in factor_and_scf (3.5 .. 12 eV)
     int krylov_force_it = 5;          // ... or at this SCF iteration at the latest
     // FP64-equivalent updates on the tcgen05 tensor cores (kernels_ozaki.cu): int8 slices per operand, 0 = DMMA only
-    int ozaki_slices = 0;             // CHEQ_OZAKI: 4..8 (7 = 54 bits per entry relative to its row maximum: fp64 grade)
-    int ozaki_slices_r = 0;           // CHEQ_OZAKI_R: slices while building the frozen factor's R (a preconditioner, kept in
-                                      // fp32 afterwards); 0 = as CHEQ_OZAKI
-    int ozaki_min_k = 1024;           // CHEQ_OZAKI_MIN_K: shallower updates stay on DMMA (slicing + epilogue do not amortise)
+    int ozaki_slices = 7;             // CHEQ_OZAKI: 0 = off, 4..8 (7 = 54 bits per entry relative to its row maximum: fp64
+                                      // grade; measured on S20k: charges 9e-12 e from the CPU oracle, DMMA 1.4e-13, 8 slices 4e-14)
+    int ozaki_slices_r = 5;           // CHEQ_OZAKI_R: slices while building the frozen factor's R (a preconditioner, kept in
+                                      // fp32 afterwards: 38 bits are plenty); 0 = as CHEQ_OZAKI
+    int ozaki_min_k = 512;            // CHEQ_OZAKI_MIN_K: shallower updates stay on DMMA (slicing + epilogue do not amortise;
+                                      // S20k: 0.1957 / 0.1909 / 0.1961 s with 1024 / 512 / 256)
     int ozaki_now = 0;                // slices in force for the launches being issued
     DeviceBuffer oz_ws, oz_err;
     int* h_oz_err = nullptr;          // pinned
-    uint64_t oz_launches = 0;
     int matfree_restart = 160;        // CHEQ_MATFREE_RESTART: GMRES restart length of the matrix-free path
     int matfree_max_steps = 4000;     // CHEQ_MATFREE_MAX_STEPS: operator applications per SCF iteration
     double matfree_tol = 1e-12;       // CHEQ_MATFREE_TOL: |P (b - K x)| <= tol |x|
@@ -291,7 +305,7 @@ struct cheq_ctx {
     cudaEvent_t ev[8]{};
     uint64_t launches = 0;
     // optional per-launch timing of the dominant kernel (gemm_nt_kernel) with CUDA events on the stream
-    std::map<std::tuple<int, int, int, int>, SplitPlan> plans;   // (mt_total, j_begin, j_end, batch)
+    std::map<std::tuple<int, int, int, int, int>, SplitPlan> plans;   // (mt_total, j_begin, j_end, batch, tcgen05 setting)
     bool profile = false;
     std::vector<cudaEvent_t> prof_events;   // pairs (start, stop)
     std::vector<int> prof_cat;              // category of each pair: 0 GEMM, 1 diagonal-tile factorisation, 2 back substitution
@@ -606,12 +620,24 @@ int prof_end(cheq_ctx* ctx) {
 }
 
 int launch_gemm_timed(cheq_ctx* ctx, const GemmArgs& g, int mt, int nt, int batch, double flops) {
-    int rc = prof_begin(ctx, 0);
-    if (rc) return rc;
     // deep single-frame updates go to the tcgen05 tensor cores as int8 slice products (kernels_ozaki.cu)
     const int S = ctx->ozaki_now;
-    if (S > 0 && batch == 1 && g.subtract && !g.n_list && g.n_peers == 0 && g.K >= ctx->ozaki_min_k &&
-        ctx->cur == ctx->stream && ozaki_supported(S, std::min(g.K, kOzakiMaxK))) {
+    bool oz = S > 0 && batch == 1 && g.subtract && !g.n_list && g.n_peers == 0 && g.K >= ctx->ozaki_min_k &&
+              ctx->cur == ctx->stream && ozaki_supported(S, std::min(g.K, kOzakiMaxK));
+    if (oz) {
+        const size_t need = ozaki_workspace_bytes(S, mt, nt, std::min(g.K, kOzakiMaxK));
+        if (need > ctx->oz_ws.cap) {
+            CU(cudaStreamSynchronize(ctx->cur));   // earlier launches may still read the old workspace
+            if (ctx->oz_ws.ensure(need) != cudaSuccess) {
+                cudaGetLastError();                // no room for the slices: this solve stays on DMMA
+                ctx->ozaki_now = 0;
+                oz = false;
+            }
+        }
+    }
+    int rc = prof_begin(ctx, oz ? 3 : 0);
+    if (rc) return rc;
+    if (oz) {
         // K is cut into chunks whose int32 group sums cannot overflow; each chunk has its own row scales
         for (int k0 = 0; k0 < g.K; k0 += kOzakiMaxK) {
             GemmArgs c = g;
@@ -622,15 +648,12 @@ int launch_gemm_timed(cheq_ctx* ctx, const GemmArgs& g, int mt, int nt, int batc
                 c.neg_cnt = g.neg_cnt + k0 / kTile;
                 c.neg_idx = g.neg_idx + k0;
             }
-            const size_t need = ozaki_workspace_bytes(S, mt, nt, c.K);
-            if (need > ctx->oz_ws.cap) {
-                CU(cudaStreamSynchronize(ctx->cur));   // earlier launches may still read the old workspace
-                CU(ctx->oz_ws.ensure(need));
-            }
             LAUNCH(launch_gemm_ozaki(c, mt, nt, S, ctx->oz_ws.p, ctx->oz_ws.cap, ctx->oz_err.as<int>(), ctx->cur));
             ctx->launches += 4;   // two row-maximum and two slicing kernels ride along
-            ctx->oz_launches++;
+            ctx->stats.tc_gemm_launches++;
         }
+        ctx->stats.tc_gemm_flops += flops;
+        ctx->stats.tc_gemm_ops += flops * (S * (S + 1) / 2);
     } else {
         LAUNCH(launch_gemm_nt(g, mt, nt, batch, ctx->cur));
     }
@@ -644,12 +667,13 @@ int launch_gemm_timed(cheq_ctx* ctx, const GemmArgs& g, int mt, int nt, int batc
 
 const SplitPlan* get_plan(cheq_ctx* ctx, int MT, int j_begin, int j_end, int batch) {
     if (j_end - j_begin < 2) return nullptr;
-    auto key = std::make_tuple(MT / kTile, j_begin / kTile, j_end / kTile, batch);
+    const bool oz = ctx->ozaki_now > 0 && batch == 1 && ctx->cur == ctx->stream;
+    auto key = std::make_tuple(MT / kTile, j_begin / kTile, j_end / kTile, batch, oz ? ctx->ozaki_now * 100000 + ctx->ozaki_min_k : 0);
     auto it = ctx->plans.find(key);
     if (it == ctx->plans.end()) {
         if (ctx->plans.size() > 64) ctx->plans.clear();
         it = ctx->plans.emplace(key, SplitPlan()).first;
-        it->second.build(MT / kTile, j_begin / kTile, j_end / kTile, batch);
+        it->second.build(MT / kTile, j_begin / kTile, j_end / kTile, batch, oz ? ctx->ozaki_now : 0, ctx->ozaki_min_k);
     }
     return &it->second;
 }
@@ -1571,7 +1595,7 @@ int krylov_build_R(Dense& D, Krylov& K, int h0, int j0, int n) {
 int krylov_freeze(cheq_ctx* ctx, Dense& D, Krylov& K, int nxp, const double* d_of_factor) {
     cudaStream_t st = ctx->stream;
     LAUNCH(launch_set_identity_tiles(K.R + (long)K.ra * kTile, (long)(K.rb - K.ra) * kTile, K.nt, K.ra, K.rb, st));
-    if (ctx->ozaki_slices_r) ctx->ozaki_now = ctx->ozaki_slices_r;
+    if (ctx->ozaki_slices > 0 && ctx->ozaki_slices_r > 0) ctx->ozaki_now = ctx->ozaki_slices_r;
     int rc = krylov_build_R(D, K, nxp, 0, K.nhp);
     ctx->ozaki_now = ctx->ozaki_slices;
     if (rc) return rc;
@@ -2785,24 +2809,25 @@ int solve_impl(cheq_ctx* ctx, const SolveIO& io) {
     }
     ctx->stats.kernel_launches = ctx->launches;
     if (ctx->profile) {
-        double ms_sum[3] = {0.0, 0.0, 0.0};
+        double ms_sum[4] = {0.0, 0.0, 0.0, 0.0};
         uint64_t n_gemm = 0;
         FILE* log = nullptr;
         if (const char* path = getenv("CHEQ_GEMM_LOG")) log = fopen(path, "w");
-        if (log) fprintf(log, "K,m_tiles,n_tiles,flops,ms\n");
+        if (log) fprintf(log, "K,m_tiles,n_tiles,flops,ms,tcgen05\n");
         for (size_t i = 0; i + 1 < ctx->prof_used; i += 2) {
             float ms = 0;
             cudaEventElapsedTime(&ms, ctx->prof_events[i], ctx->prof_events[i + 1]);
             const int cat = ctx->prof_cat[i / 2];
             ms_sum[cat] += ms;
-            n_gemm += (cat == 0);
-            if (log && cat == 0) {
+            n_gemm += (cat == 0 || cat == 3);
+            if (log && (cat == 0 || cat == 3)) {
                 const auto& sh = ctx->prof_shape[i / 2];
-                fprintf(log, "%d,%d,%d,%.6e,%.6f\n", sh.K, sh.mt, sh.nt, sh.flops, ms);
+                fprintf(log, "%d,%d,%d,%.6e,%.6f,%d\n", sh.K, sh.mt, sh.nt, sh.flops, ms, cat == 3 ? 1 : 0);
             }
         }
         if (log) fclose(log);
-        ctx->stats.gemm_ms = ms_sum[0];
+        ctx->stats.gemm_ms = ms_sum[0] + ms_sum[3];
+        ctx->stats.tc_gemm_ms = ms_sum[3];
         ctx->stats.gemm_launches = n_gemm;
         ctx->stats.gemm_flops = ctx->prof_flops;
         ctx->stats.potrf_ms = ms_sum[1];
@@ -2875,16 +2900,14 @@ int32_t cheq_ctx_create(int32_t device, cheq_ctx** out) {
     if (const char* env = getenv("CHEQ_OZAKI_MIN_K")) ctx->ozaki_min_k = std::max(128, atoi(env));
     if (ctx->ozaki_slices != 0 && (ctx->ozaki_slices < 4 || ctx->ozaki_slices > 8)) ctx->ozaki_slices = 7;
     if (ctx->ozaki_slices_r != 0 && (ctx->ozaki_slices_r < 4 || ctx->ozaki_slices_r > 8)) ctx->ozaki_slices_r = 0;
-    if (ctx->ozaki_slices || ctx->ozaki_slices_r) {
-        if (configure_ozaki_kernels() != cudaSuccess || ctx->oz_err.ensure(64) != cudaSuccess ||
-            cudaMemset(ctx->oz_err.p, 0, 64) != cudaSuccess ||
-            cudaMallocHost((void**)&ctx->h_oz_err, sizeof(int)) != cudaSuccess) {
-            cudaGetLastError();
-            cheq_ctx_destroy(ctx);
-            return CHEQ_ERR_CUDA;
-        }
-        *ctx->h_oz_err = 0;
+    if (configure_ozaki_kernels() != cudaSuccess || ctx->oz_err.ensure(64) != cudaSuccess ||
+        cudaMemset(ctx->oz_err.p, 0, 64) != cudaSuccess ||
+        cudaMallocHost((void**)&ctx->h_oz_err, sizeof(int)) != cudaSuccess) {
+        cudaGetLastError();
+        cheq_ctx_destroy(ctx);
+        return CHEQ_ERR_CUDA;
     }
+    *ctx->h_oz_err = 0;
     ctx->ozaki_now = ctx->ozaki_slices;
     if (const char* env = getenv("CHEQ_MORTON")) ctx->morton = atoi(env) != 0;
     if (const char* env = getenv("CHEQ_MATFREE_RESTART")) ctx->matfree_restart = atoi(env);
@@ -3016,6 +3039,18 @@ int32_t cheq_set_krylov(cheq_ctx* ctx, int32_t enabled, int32_t min_hydrogen, do
     if (freeze_ev > 0.0) ctx->krylov_freeze_ev = freeze_ev;
     else if (freeze_ev < 0.0) ctx->krylov_freeze_ev = 0.0;   // back to the cost model
     if (force_iteration > 0) ctx->krylov_force_it = std::max(2, (int)force_iteration);
+    return CHEQ_OK;
+}
+
+int32_t cheq_set_ozaki(cheq_ctx* ctx, int32_t slices, int32_t slices_r, int32_t min_k) {
+    if (!ctx) return CHEQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if ((slices > 0 && (slices < 4 || slices > 8)) || (slices_r > 0 && (slices_r < 4 || slices_r > 8)))
+        return fail(ctx, CHEQ_ERR_INVALID_ARGUMENT, "slice counts must be 0 (off / same) or 4..8");
+    if (slices >= 0) ctx->ozaki_slices = slices;
+    if (slices_r >= 0) ctx->ozaki_slices_r = slices_r;
+    if (min_k > 0) ctx->ozaki_min_k = std::max(128, (int)min_k);
+    ctx->ozaki_now = ctx->ozaki_slices;
     return CHEQ_OK;
 }
 
@@ -3325,6 +3360,59 @@ int32_t cheq_dbg_gemm_nt(cheq_ctx* ctx, uint64_t m, uint64_t n, uint64_t k, cons
     LAUNCH(launch_gemm_nt(g, (int)(m / kTile), (int)(n / kTile), 1, st));
     CU(cudaMemcpyAsync(c, ctx->misc2.p, m * n * 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));
+    return CHEQ_OK;
+}
+
+int32_t cheq_dbg_gemm_ozaki(cheq_ctx* ctx, uint64_t m, uint64_t n, uint64_t k, const double* a, const double* b,
+                            double* c, int32_t subtract, int32_t lower, int32_t slices, const double* signs) {
+    if (!ctx) return CHEQ_ERR_INVALID_ARGUMENT;
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    ctx->err.clear();
+    if (m % kTile || n % kTile || k % kTile || !m || !n || !k)
+        return fail(ctx, CHEQ_ERR_INVALID_ARGUMENT, "m, n, k must be positive multiples of 128");
+    if (!ozaki_supported(slices, (int)std::min<uint64_t>(k, kOzakiMaxK)) || k > (uint64_t)kOzakiMaxK)
+        return fail(ctx, CHEQ_ERR_INVALID_ARGUMENT, "4..8 slices, k at most 8192 per launch");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CU(ctx->misc0.ensure(m * k * 8));
+    CU(ctx->misc1.ensure(n * k * 8));
+    CU(ctx->misc2.ensure(m * n * 8));
+    CU(cudaMemcpyAsync(ctx->misc0.p, a, m * k * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->misc1.p, b, n * k * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(ctx->misc2.p, c, m * n * 8, cudaMemcpyHostToDevice, st));
+    // pivot signs as the factorisation stores them: per 128-wide tile of K a count and the in-tile indices
+    std::vector<int> flags((size_t)(k / kTile) * (kTile + 1), 0);
+    int* cnt = flags.data();
+    int* idx = flags.data() + k / kTile;
+    if (signs)
+        for (uint64_t i = 0; i < k; ++i)
+            if (signs[i] < 0.0) idx[(i / kTile) * kTile + cnt[i / kTile]++] = (int)(i % kTile);
+    CU(ctx->sgn_flags.ensure(flags.size() * sizeof(int)));
+    CU(cudaMemcpyAsync(ctx->sgn_flags.p, flags.data(), flags.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    GemmArgs g{};
+    g.A = ctx->misc0.as<double>();
+    g.lda = (long)m;
+    g.B = ctx->misc1.as<double>();
+    g.ldb = (long)n;
+    g.C = ctx->misc2.as<double>();
+    g.ldc = (long)m;
+    g.K = (int)k;
+    g.lower = lower ? 1 : 0;
+    g.subtract = subtract ? 1 : 0;
+    if (signs) {
+        g.neg_cnt = ctx->sgn_flags.as<int>();
+        g.neg_idx = ctx->sgn_flags.as<int>() + k / kTile;
+    }
+    const int mt = (int)(m / kTile), nt = (int)(n / kTile);
+    CU(ctx->oz_ws.ensure(ozaki_workspace_bytes(slices, mt, nt, (int)k)));
+    LAUNCH(launch_gemm_ozaki(g, mt, nt, slices, ctx->oz_ws.p, ctx->oz_ws.cap, ctx->oz_err.as<int>(), st));
+    CU(cudaMemcpyAsync(c, ctx->misc2.p, m * n * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaMemcpyAsync(ctx->h_oz_err, ctx->oz_err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (*ctx->h_oz_err) {
+        cudaMemsetAsync(ctx->oz_err.p, 0, sizeof(int), st);
+        return fail(ctx, CHEQ_ERR_CUDA, "tcgen05 slice-product pipeline timed out");
+    }
     return CHEQ_OK;
 }
 

@@ -65,15 +65,13 @@ constexpr int kGroupM = 8;   // tile rows per rasterisation group: their A slabs
 // FM = 16-row fragments per warp, WM = warps along M: CTA tile (16 FM WM) x 128.
 //   <4, 2>: 128 x 128, 8 warps (64 x 32 warp tiles)      <2, 4>: 128 x 128, 16 warps (32 x 32)
 //   <2, 2>:  64 x 128, 8 warps: twice the CTAs for skinny updates that would otherwise leave SMs idle
-template <int FM, int WM, bool PEERS = false, int WN = 4, int FN = 2, int KB = BK, int NST = STAGES, int MINB = 1>
-__global__ void __launch_bounds__(WM * WN * 32, MINB) gemm_nt_kernel(GemmArgs g) {
-    static_assert(WN * FN * 16 == BN, "the CTA tile is always 128 columns wide");
+template <int FM, int WM, bool PEERS = false>
+__global__ void __launch_bounds__(WM * 4 * 32, 1) gemm_nt_kernel(GemmArgs g) {
     constexpr int kWarpsM = WM;
-    constexpr int kThreads = kWarpsM * WN * 32;       // 128, 256 or 512
+    constexpr int kThreads = kWarpsM * 4 * 32;        // 256 or 512
     constexpr int TM = 16 * FM * WM;                  // CTA tile rows: 128 or 64
-    constexpr int kChunksA = TM * KB / 2 / kThreads;  // 16-byte chunks per thread per stage, A slab (TM x KB)
-    constexpr int kChunksB = 64 * KB / kThreads;      //                                      B slab (128 x KB)
-    constexpr int LDA_S = (TM == 128) ? LDT : TM + 4;   // padded row stride of the A slab (conflict-free LDS.128)
+    constexpr int kChunksA = TM * BK / 2 / kThreads;  // 16-byte chunks per thread per stage, A slab (TM x BK)
+    constexpr int kChunksB = 64 * BK / kThreads;      //                                      B slab (128 x BK)
     // grouped rasterisation: consecutive CTAs walk the tile columns of a group of kGroupM tile rows
     const int frame = blockIdx.z;
     int tile_m, tile_n;
@@ -90,26 +88,26 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) gemm_nt_kernel(GemmArgs g)
     if (g.lower && g.row0 + tile_m * TM + TM - 1 < tile_n * BN) return;   // tile entirely above the diagonal
     if (g.state && !g.state[frame].active) return;
     extern __shared__ __align__(16) double smem[];
-    double* As = smem;                          // [NST][KB][LDA_S]
-    double* Bs = smem + NST * KB * LDA_S;       // [NST][KB][LDT]
+    double* As = smem;                          // [STAGES][BK][LDT]
+    double* Bs = smem + STAGES * BK * LDT;      // [STAGES][BK][LDT]
 
     const double* A = g.A + (long)frame * g.strideA + (long)tile_m * TM;
     const double* B = g.B + (long)frame * g.strideB + (long)tile_n * BN;
     double* C = g.C + (long)frame * g.strideC + (long)tile_m * TM + (long)tile_n * BN * g.ldc;
 
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-    const int wm = warp % kWarpsM, wn = warp / kWarpsM;   // kWarpsM x WN warps, warp tile (16 FM) x (16 FN)
+    const int wm = warp % kWarpsM, wn = warp / kWarpsM;   // kWarpsM x 4 warps, warp tile (16 FM) x 32
     const int gq = lane >> 2, q = lane & 3;
 
     auto load_stage = [&](int stage, int ktile) {
-        double* as = As + stage * KB * LDA_S;
-        double* bs = Bs + stage * KB * LDT;
-        const long k0 = (long)ktile * KB;
+        double* as = As + stage * BK * LDT;
+        double* bs = Bs + stage * BK * LDT;
+        const long k0 = (long)ktile * BK;
 #pragma unroll
         for (int i = 0; i < kChunksA; ++i) {
             const int c = t + i * kThreads;
             const int kr = c / (TM / 2), mc = c % (TM / 2);
-            cp_async16(as + kr * LDA_S + 2 * mc, A + 2 * mc + (k0 + kr) * g.lda);
+            cp_async16(as + kr * LDT + 2 * mc, A + 2 * mc + (k0 + kr) * g.lda);
         }
 #pragma unroll
         for (int i = 0; i < kChunksB; ++i) {
@@ -119,39 +117,39 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) gemm_nt_kernel(GemmArgs g)
         }
     };
 
-    double acc[FM][2][FN][2][2];  // [fm][row parity][fn][col parity][e]
+    double acc[FM][2][2][2][2];  // [fm][row parity][fn][col parity][e]
 #pragma unroll
-    for (int i = 0; i < FM * FN * 8; ++i) ((double*)acc)[i] = 0.0;
+    for (int i = 0; i < FM * 16; ++i) ((double*)acc)[i] = 0.0;
 
-    const int kt = g.K / KB;
+    const int kt = g.K / BK;
 #pragma unroll
-    for (int s = 0; s < NST - 1; ++s) {
+    for (int s = 0; s < STAGES - 1; ++s) {
         if (s < kt) load_stage(s, s);
         cp_async_commit();
     }
 
     for (int it = 0; it < kt; ++it) {
-        cp_async_wait<NST - 2>();
+        cp_async_wait<STAGES - 2>();
         __syncthreads();
         {
-            const int nxt = it + NST - 1;
-            if (nxt < kt) load_stage(nxt % NST, nxt);
+            const int nxt = it + STAGES - 1;
+            if (nxt < kt) load_stage(nxt % STAGES, nxt);
             cp_async_commit();
         }
-        const int stage = it % NST;
-        const double* as = As + stage * KB * LDA_S + wm * (16 * FM) + 2 * gq;
-        const double* bs = Bs + stage * KB * LDT + wn * (16 * FN) + 2 * gq;
+        const int stage = it % STAGES;
+        const double* as = As + stage * BK * LDT + wm * (16 * FM) + 2 * gq;
+        const double* bs = Bs + stage * BK * LDT + wn * 32 + 2 * gq;
 #pragma unroll
-        for (int kk = 0; kk < KB / 4; ++kk) {
-            double2 a[FM], b[FN];
+        for (int kk = 0; kk < BK / 4; ++kk) {
+            double2 a[FM], b[2];
 #pragma unroll
-            for (int fm = 0; fm < FM; ++fm) a[fm] = *(const double2*)(as + (kk * 4 + q) * LDA_S + fm * 16);
+            for (int fm = 0; fm < FM; ++fm) a[fm] = *(const double2*)(as + (kk * 4 + q) * LDT + fm * 16);
 #pragma unroll
-            for (int fn = 0; fn < FN; ++fn) b[fn] = *(const double2*)(bs + (kk * 4 + q) * LDT + fn * 16);
+            for (int fn = 0; fn < 2; ++fn) b[fn] = *(const double2*)(bs + (kk * 4 + q) * LDT + fn * 16);
 #pragma unroll
             for (int fm = 0; fm < FM; ++fm)
 #pragma unroll
-                for (int fn = 0; fn < FN; ++fn) {
+                for (int fn = 0; fn < 2; ++fn) {
                     dmma884(acc[fm][0][fn][0][0], acc[fm][0][fn][0][1], a[fm].x, b[fn].x);
                     dmma884(acc[fm][0][fn][1][0], acc[fm][0][fn][1][1], a[fm].x, b[fn].y);
                     dmma884(acc[fm][1][fn][0][0], acc[fm][1][fn][0][1], a[fm].y, b[fn].x);
@@ -170,20 +168,20 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) gemm_nt_kernel(GemmArgs g)
             for (int j = 0; j < nneg; ++j) {
                 const long k = (long)kt128 * kTile + idx[kt128 * kTile + j];
                 const double* ak = A + k * g.lda + wm * (16 * FM) + 2 * gq;
-                const double* bk = B + k * g.ldb + wn * (16 * FN) + 4 * q;
+                const double* bk = B + k * g.ldb + wn * 32 + 4 * q;
                 double2 av[FM];
-                double bv[FN][2][2];   // [fn][pc][e]: column 4 q + 2 e + pc of the 16-column group
+                double bv[2][2][2];   // [fn][pc][e]: column 4 q + 2 e + pc of the 16-column group
 #pragma unroll
                 for (int fm = 0; fm < FM; ++fm) av[fm] = *(const double2*)(ak + fm * 16);
 #pragma unroll
-                for (int fn = 0; fn < FN; ++fn) {
+                for (int fn = 0; fn < 2; ++fn) {
                     const double2 lo = *(const double2*)(bk + fn * 16), hi = *(const double2*)(bk + fn * 16 + 2);
                     bv[fn][0][0] = lo.x; bv[fn][1][0] = lo.y; bv[fn][0][1] = hi.x; bv[fn][1][1] = hi.y;
                 }
 #pragma unroll
                 for (int fm = 0; fm < FM; ++fm)
 #pragma unroll
-                    for (int fn = 0; fn < FN; ++fn)
+                    for (int fn = 0; fn < 2; ++fn)
 #pragma unroll
                         for (int pc = 0; pc < 2; ++pc)
 #pragma unroll
@@ -201,12 +199,12 @@ __global__ void __launch_bounds__(WM * WN * 32, MINB) gemm_nt_kernel(GemmArgs g)
     for (int fm = 0; fm < FM; ++fm) {
         const int row = wm * (16 * FM) + fm * 16 + 2 * gq;
 #pragma unroll
-        for (int fn = 0; fn < FN; ++fn)
+        for (int fn = 0; fn < 2; ++fn)
 #pragma unroll
             for (int pc = 0; pc < 2; ++pc)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) {
-                    const int col = wn * (16 * FN) + fn * 16 + 4 * q + 2 * e + pc;
+                    const int col = wn * 32 + fn * 16 + 4 * q + 2 * e + pc;
                     double2* p = (double2*)(C + row + (long)col * g.ldc);
                     double2 v = make_double2(acc[fm][0][fn][pc][e], acc[fm][1][fn][pc][e]);
                     if (g.subtract) {
@@ -837,11 +835,6 @@ cudaError_t potrf_debug_cycles(unsigned long long* out, int reset) {
     return e;
 }
 
-// Variant 1 (CHEQ_GEMM_VARIANT=1): 64 x 128 CTA tile, 4 warps with 32 x 64 warp tiles (32 DMMA per 6 LDS.128 instead
-// of 16 per 4), 16-deep slabs x 4 stages = 100 KB -> TWO CTAs per SM, whose prologues / epilogues overlap each
-// other's main loops (the shape cuBLAS picks for DGEMM on this part: 64x128_16x3).
-constexpr int kGemmSmemV1 = 4 * 16 * (68 + LDT) * (int)sizeof(double);   // 102400 B
-int g_gemm_variant = [] { const char* e = getenv("CHEQ_GEMM_VARIANT"); return e ? atoi(e) : 0; }();
 int g_gemm_warps = 16;        // warps per 128 x 128 GEMM CTA: 8 (64 x 32 warp tiles) or 16 (32 x 32)
 int g_gemm_half_tiles = -1;   // -1: heuristic; 0 / 1: force 128- / 64-row tiles (tuning)
 void set_gemm_warps(int w) {
@@ -863,9 +856,6 @@ cudaError_t configure_dense_kernels() {
         e = cudaFuncSetAttribute(gemm_nt_kernel<2, 2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(gemm_nt_kernel<2, 4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(gemm_nt_kernel<2, 2, false, 2, 4, 16, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kGemmSmemV1);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPotrfSmem);
     if (e == cudaSuccess)
@@ -892,11 +882,7 @@ cudaError_t launch_gemm_nt(const GemmArgs& g, int m_tiles, int n_tiles, int batc
         }
         return cudaGetLastError();
     }
-    if (g_gemm_variant == 1 && !half) {
-        args.m_tiles = 2 * m_tiles;
-        grid.x = 2 * m_tiles * n_tiles;
-        gemm_nt_kernel<2, 2, false, 2, 4, 16, 4, 2><<<grid, 128, kGemmSmemV1, stream>>>(args);
-    } else if (half) {
+    if (half) {
         args.m_tiles = 2 * m_tiles;
         grid.x = 2 * m_tiles * n_tiles;
         gemm_nt_kernel<2, 2><<<grid, 256, kGemmSmem, stream>>>(args);

@@ -168,6 +168,19 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
     volatile int* dead = &dead_s;
     const uint32_t smem0 = oz_smem_u32(oz_smem);
 
+    // Every thread owns one row of the C tile.  Its 64 old values are fetched NOW, so that their latency hides behind
+    // the main loop instead of sitting in the epilogue (which no other CTA on this SM can overlap: TMEM is full).
+    const long row = (long)tile_m * kOzTM + t;
+    double* crow = a.C + row + (long)tile_n * kOzTN * a.ldc;
+    double cold[kOzTN];
+    if (a.subtract) {
+#pragma unroll
+        for (int j = 0; j < kOzTN; ++j) cold[j] = __ldcg(crow + (long)j * a.ldc);
+    } else {
+#pragma unroll
+        for (int j = 0; j < kOzTN; ++j) cold[j] = 0.0;
+    }
+
     if (t == 0) {
         // ---- producer: two bulk copies per stage ----
         const int8_t* ga = a.PA + (size_t)tile_m * a.nkb * kStageA;
@@ -208,12 +221,10 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
     const bool ready = oz_wait(oz_smem_u32(&tmem_bar), 0u, dead, a.error, 3);
     asm volatile("tcgen05.fence::after_thread_sync;\n");
     if (ready && !*dead) {
-        const long row = (long)tile_m * kOzTM + t;
         const double sar = a.sa[row];
         const double* sb = a.sb + (long)tile_n * kOzTN;
-        double* crow = a.C + row + (long)tile_n * kOzTN * a.ldc;
         const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-#pragma unroll 1
+#pragma unroll
         for (int c = 0; c < kOzTN; c += 8) {
             uint32_t v[S][8];
 #pragma unroll
@@ -229,8 +240,7 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
 #pragma unroll
                 for (int g = S - 2; g >= 0; --g) acc = fma(acc, 1.0 / 256.0, (double)(int)v[g][j]);
                 const double val = acc * sar * sb[c + j];
-                double* p = crow + (long)(c + j) * a.ldc;
-                *p = a.subtract ? *p - val : val;
+                crow[(long)(c + j) * a.ldc] = a.subtract ? cold[c + j] - val : val;
             }
         }
     }
@@ -341,7 +351,7 @@ cudaError_t oz_launch_t(const GemmArgs& g, int m_tiles, int n_tiles, void* ws, s
     if (off + (size_t)S * (m + n) * K > ws_bytes) return cudaErrorInvalidValue;
     cudaError_t e = cudaMemsetAsync(mxa, 0, (size_t)(m + n) * 8, stream);
     if (e != cudaSuccess) return e;
-    const int kchunk = 512, ksplit = (K + kchunk - 1) / kchunk;
+    const int kchunk = 128, ksplit = (K + kchunk - 1) / kchunk;
     oz_rowmax_kernel<<<dim3((unsigned)(m / 128), ksplit), 128, 0, stream>>>(g.A, g.lda, K, kchunk, mxa);
     oz_rowmax_kernel<<<dim3((unsigned)(n / 128), ksplit), 128, 0, stream>>>(g.B, g.ldb, K, kchunk, mxb);
     oz_slice_kernel<S, kOzTM><<<dim3((unsigned)(m / kOzTM), K / 128), 256, 0, stream>>>(g.A, g.lda, K, mxa, sa, PA,

@@ -71,6 +71,13 @@ class Context:
         if rc != _ffi.OK:
             raise CheqError(f"cheq_set_krylov failed with status {rc}")
 
+    def set_ozaki(self, slices: int = -1, slices_r: int = -1, min_k: int = 0):
+        """FP64-equivalent updates on the tcgen05 tensor cores (int8 slice products): slices = 0 switches the path off,
+        4..8 slices per operand entry (7 = fp64 grade, the default); negative / zero arguments keep the setting."""
+        rc = self._lib.cheq_set_ozaki(self.handle, int(slices), int(slices_r), int(min_k))
+        if rc != _ffi.OK:
+            raise CheqError(f"cheq_set_ozaki failed with status {rc}: {self.last_error()}")
+
 
 _default_ctx = {}
 _default_lock = threading.Lock()

@@ -99,6 +99,11 @@ typedef struct cheq_stats {
     /* matrix-free path (cheq_solve_iterative): operator applications and the pair integrals they recomputed */
     uint64_t matfree_matvecs;
     double matfree_pairs;
+    /* updates executed on the tcgen05 tensor cores as int8 slice products (FP64-equivalent, see cheq_set_ozaki) */
+    uint64_t tc_gemm_launches;
+    double tc_gemm_flops;    /* algorithmic FP64 flops of those launches */
+    double tc_gemm_ops;      /* int8 tensor operations they stand for: flops x slice products per entry, S (S + 1) / 2 */
+    double tc_gemm_ms;       /* their summed duration incl. the slicing passes (only with cheq_set_profiling) */
 } cheq_stats;
 
 int32_t cheq_ctx_create(int32_t device, cheq_ctx** out);
@@ -124,6 +129,14 @@ int32_t cheq_get_scf_trace(const cheq_ctx* ctx, uint32_t capacity, double* delta
  * current setting; freeze_ev < 0 selects the built-in cost model (the default: 3.5 .. 12 eV depending on the size of the
  * hydrogen block and the number of GPUs). */
 int32_t cheq_set_krylov(cheq_ctx* ctx, int32_t enabled, int32_t min_hydrogen, double freeze_ev, int32_t force_iteration);
+/* FP64-equivalent updates on the tcgen05 tensor cores.  tcgen05.mma has no f64 kind; deep
+ * single-frame updates C -= A S B^T of the factorisation are therefore run as exact int8 slice products (Ozaki
+ * split: `slices` base-256 digits per entry relative to the largest magnitude of its row, int32 accumulators in TMEM,
+ * fp64 recombination).  slices: 0 = off (every update on the FP64 DMMA path), 4..8 (7, the default, carries 54 bits);
+ * slices_r: the count used while building the frozen factor's R = L^-T S, which only preconditions GMRES (0 = same as
+ * slices; default 5); min_k: updates shallower than this stay on DMMA (default 512).  Negative / zero arguments keep
+ * the current setting (slices = 0 switches the path off).  Env: CHEQ_OZAKI, CHEQ_OZAKI_R, CHEQ_OZAKI_MIN_K. */
+int32_t cheq_set_ozaki(cheq_ctx* ctx, int32_t slices, int32_t slices_r, int32_t min_k);
 
 /* ---- multi-GPU: one dense system across the GPUs of a node ----------------------------
  * The reference is single-node CPU code (rayon, implementation.rs:394, 491) and has no equivalent; this is the
@@ -225,6 +238,11 @@ int32_t cheq_dbg_cholesky_solve(cheq_ctx* ctx, uint64_t n, const double* a, uint
                                 double* x_out, double* l_out /* nullable, n x n */);
 int32_t cheq_dbg_gemm_nt(cheq_ctx* ctx, uint64_t m, uint64_t n, uint64_t k, const double* a,
                          const double* b, double* c, int32_t subtract);
+/* The same product through the tcgen05 int8 slice path (cheq_set_ozaki): C <- C - A S B^T (subtract != 0) or
+ * A S B^T, S = diag(signs) (nullable: identity; entries +-1), `lower` != 0 skips the 128 x 64 tiles entirely above the
+ * diagonal; slices 4..8, k <= 8192. */
+int32_t cheq_dbg_gemm_ozaki(cheq_ctx* ctx, uint64_t m, uint64_t n, uint64_t k, const double* a, const double* b,
+                            double* c, int32_t subtract, int32_t lower, int32_t slices, const double* signs);
 /* Times `reps` launches of the same GEMM on device-resident operands (CUDA events); ms_out = ms per launch.
  * lower != 0 skips the tiles above the diagonal (the symmetric trailing update). */
 int32_t cheq_dbg_gemm_bench(cheq_ctx* ctx, uint64_t m, uint64_t n, uint64_t k, int32_t lower, int32_t subtract,

@@ -68,6 +68,8 @@ extern "C" {
     pub fn cheq_set_krylov(
         ctx: *mut cheq_ctx, enabled: i32, min_hydrogen: i32, freeze_ev: f64, force_iteration: i32,
     ) -> i32;
+    /// FP64-equivalent updates on the tcgen05 tensor cores (int8 slice products): 0 = off, 4..8 slices (7 = fp64 grade).
+    pub fn cheq_set_ozaki(ctx: *mut cheq_ctx, slices: i32, slices_r: i32, min_k: i32) -> i32;
     pub fn cheq_solve_batch(
         ctx: *mut cheq_ctx, n_frames: u64, n_atoms: u64, xyz: *const f64, chi: *const f64,
         hardness: *const f64, radius: *const f64, n_quantum: *const u8, total_charge: f64,

@@ -64,8 +64,18 @@ def test_s20k_full_scf_parity_vs_oracle(gpu_ctx, s20k_oracle):
     # default path: stale-factor iterations on
     gpu_ctx.set_krylov(True)
     res, trace, st = solve_arrays(gpu_ctx, Z, xyz)
-    report["default"] = assert_trajectory(res, trace, ref, "S20k default (stale factor + GMRES)")
+    report["default"] = assert_trajectory(res, trace, ref, "S20k default (tcgen05 slice products + stale factor + GMRES)")
     assert st["krylov_iterations"] > 0 and st["lu_fallback_frames"] == 0
+    assert st["tc_gemm_launches"] > 0 and st["tc_gemm_flops"] > 0.5 * st["flops_factor"]
+    # every update on the FP64 DMMA path (the tcgen05 int8 slice path off), and with 8 slices instead of 7
+    gpu_ctx.set_ozaki(0)
+    res, trace, st = solve_arrays(gpu_ctx, Z, xyz)
+    report["dmma_only"] = assert_trajectory(res, trace, ref, "S20k DMMA only")
+    assert st["tc_gemm_launches"] == 0
+    gpu_ctx.set_ozaki(8, 8)
+    res, trace, st = solve_arrays(gpu_ctx, Z, xyz)
+    report["slices_8"] = assert_trajectory(res, trace, ref, "S20k 8 slices everywhere")
+    gpu_ctx.set_ozaki(7, 5)
     # round-1 path: refactor the hydrogen block every iteration
     gpu_ctx.set_krylov(False)
     res, trace, st = solve_arrays(gpu_ctx, Z, xyz)

@@ -120,6 +120,41 @@ def test_gemm_nt_dmma(gpu_ctx, m, n, k):
         assert np.max(np.abs(Cg - ref)) < 1e-11 * math.sqrt(k)
 
 
+@pytest.mark.parametrize("m,n,k,slices,lower", [(128, 128, 128, 7, 0), (384, 256, 640, 4, 0), (384, 256, 640, 5, 0),
+                                                 (384, 256, 640, 6, 0), (384, 256, 640, 7, 0), (384, 256, 640, 8, 0),
+                                                 (640, 384, 1152, 7, 1), (2560, 2560, 2048, 7, 1), (256, 128, 8192, 7, 0)])
+def test_gemm_ozaki_tcgen05(gpu_ctx, m, n, k, slices, lower):
+    """C -= A S B^T as int8 slice products on tcgen05.mma.kind::i8 (kernels_ozaki.cu): the error of an entry is
+    bounded relative to rowmax(A) * rowmax(B) * K by the slice count (54 bits at 7 slices), whatever the dynamic range
+    of the rows; pivot signs are folded into B; with `lower` the tiles above the diagonal are not touched."""
+    rng = np.random.default_rng(m + n + k + slices)
+    A = rng.normal(size=(m, k)) * np.exp(2.0 * rng.normal(size=(m, 1))) * np.exp2(-rng.integers(0, 8, size=(m, k)))
+    B = rng.normal(size=(n, k)) * np.exp(2.0 * rng.normal(size=(n, 1)))
+    A[1, :] = 0.0                      # an all-zero row
+    A[2, 3] = 1e12                     # one huge entry: the rest of that row loses relative, not absolute, accuracy
+    A, B = np.asfortranarray(A), np.asfortranarray(B)
+    C0 = np.asfortranarray(rng.normal(size=(m, n)))
+    sgn = np.where(rng.random(k) < 0.3, -1.0, 1.0)
+    scale = np.abs(A).max(axis=1)[:, None] * np.abs(B).max(axis=1)[None, :] * k
+    small = m * n * k <= 1 << 27
+    prod = ((A * sgn).astype(np.longdouble) @ B.T.astype(np.longdouble)) if small else (A * sgn) @ B.T
+    for sub in (1, 0):
+        Cg = C0.copy(order="F")
+        rc = gpu_ctx._lib.cheq_dbg_gemm_ozaki(gpu_ctx.handle, m, n, k, _ptr(A), _ptr(B), _ptr(Cg), sub, lower, slices,
+                                              _ptr(sgn))
+        assert rc == 0, gpu_ctx.last_error()
+        ref = np.asarray(C0 - prod if sub else prod, dtype=np.longdouble)
+        # beyond the slicing bound only the fp64 rounding of the recombination and of the update of C is allowed
+        err = np.maximum(np.abs(Cg - ref) - 4e-16 * (np.abs(C0) + np.abs(np.asarray(prod, dtype=np.float64))), 0.0) / (scale + 1e-300)
+        touched = np.ones((m, n), dtype=bool)
+        if lower:
+            i, j = np.indices((m, n))
+            touched = (i // 128) * 128 + 127 >= (j // 64) * 64
+            assert np.array_equal(Cg[~touched], C0[~touched])
+        bound = max(2.0 ** -(8 * slices - 6), 1e-17 if small else 2e-15 / math.sqrt(k))
+        assert float(err[touched].max()) <= bound, (float(err[touched].max()), bound)
+
+
 @pytest.mark.parametrize("n", [5, 128, 200, 515, 1300])
 def test_cholesky_solve(gpu_ctx, n):
     rng = np.random.default_rng(n)

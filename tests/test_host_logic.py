@@ -104,7 +104,7 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layouts_match_header():
     assert C.sizeof(_ffi.Options) == 32
     assert C.sizeof(_ffi.External) == 8 + 4 * 8 + 24
-    assert C.sizeof(_ffi.Stats) == 7 * 8 + 4 * 8 + 2 * 4 + 2 * 8 + 8 + 5 * 8 + 4 * 8 + 2 * 8   # + the four krylov_* and two matfree_* fields
+    assert C.sizeof(_ffi.Stats) == 7 * 8 + 4 * 8 + 2 * 4 + 2 * 8 + 8 + 5 * 8 + 4 * 8 + 2 * 8 + 4 * 8   # + the four krylov_*, two matfree_* and four tc_gemm_* fields
     o = _ffi.Options()
     _ffi.lib().cheq_options_default(C.byref(o))
     assert (o.tolerance, o.lambda_scale, o.damping_value, o.max_iterations) == (1e-6, 0.5, 0.4, 2000)
