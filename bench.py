@@ -712,7 +712,7 @@ def run_ours(args, rank, local_rank, world):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_text(name, n, iterations),
                    "parallelism": (f"one system over {world} GPUs: 1-D block-cyclic column panels ("
-                                   f"{os.environ.get('CHEQ_TILES_PER_PANEL', '4')} x 128 columns), owner-computes "
+                                   f"{os.environ.get('CHEQ_TILES_PER_PANEL', '8 (>= 4 panels per rank) or 4')} x 128 columns), owner-computes "
                                    "assembly/updates, finished panels pushed to the peers over NVLink (copy engines, "
                                    "CUDA IPC mappings, flag + cuStreamWaitValue32) up to 4 GPUs or NCCL-broadcast "
                                    "beyond, panel- and tile-level look-ahead, replicated triangular solves "

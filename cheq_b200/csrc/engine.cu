@@ -231,6 +231,8 @@ struct cheq_ctx {
     cudaEvent_t ev_ready = nullptr, ev_bcast = nullptr;
     int factor_mode = 0;                   // 0: auto (recursive on one GPU, blocked when world > 1), 1: blocked
     int tiles_per_panel = 4;
+    bool tiles_per_panel_set = false;      // chosen by the caller (API / CHEQ_TILES_PER_PANEL): no automatic widening
+    int tpp_now = 4;                       // panel width of the current plan
     PanelPlan pplan;
     DeviceBuffer stage, own_list, col_mask, chain;
     // peer-memory data plane (multi-GPU): the owner's kernels store finished panel tiles straight into the peers'
@@ -292,6 +294,8 @@ struct cheq_ctx {
     int ozaki_min_k = 512;            // CHEQ_OZAKI_MIN_K: shallower updates stay on DMMA (slicing + epilogue do not amortise;
                                       // S20k: 0.1957 / 0.1909 / 0.1961 s with 1024 / 512 / 256)
     int ozaki_now = 0;                // slices in force for the launches being issued
+    bool oz_same_a = false;           // set by a caller whose next update multiplies the SAME left operand as its previous one
+    struct { const double* A = nullptr; long lda = 0; int mt = 0, K = 0, S = 0; } oz_last;   // A operand whose planes are in oz_ws
     DeviceBuffer oz_ws, oz_err;
     int* h_oz_err = nullptr;          // pinned
     int matfree_restart = 160;        // CHEQ_MATFREE_RESTART: GMRES restart length of the matrix-free path
@@ -622,12 +626,15 @@ int prof_end(cheq_ctx* ctx) {
 int launch_gemm_timed(cheq_ctx* ctx, const GemmArgs& g, int mt, int nt, int batch, double flops) {
     // deep single-frame updates go to the tcgen05 tensor cores as int8 slice products (kernels_ozaki.cu)
     const int S = ctx->ozaki_now;
-    bool oz = S > 0 && batch == 1 && g.subtract && !g.n_list && g.n_peers == 0 && g.K >= ctx->ozaki_min_k &&
+    bool oz = S > 0 && batch == 1 && g.subtract && g.n_peers == 0 && g.K >= ctx->ozaki_min_k &&
               ctx->cur == ctx->stream && ozaki_supported(S, std::min(g.K, kOzakiMaxK));
+    const bool same_a = ctx->oz_same_a;
+    ctx->oz_same_a = false;
     if (oz) {
         const size_t need = ozaki_workspace_bytes(S, mt, nt, std::min(g.K, kOzakiMaxK));
         if (need > ctx->oz_ws.cap) {
             CU(cudaStreamSynchronize(ctx->cur));   // earlier launches may still read the old workspace
+            ctx->oz_last.A = nullptr;
             if (ctx->oz_ws.ensure(need) != cudaSuccess) {
                 cudaGetLastError();                // no room for the slices: this solve stays on DMMA
                 ctx->ozaki_now = 0;
@@ -648,7 +655,14 @@ int launch_gemm_timed(cheq_ctx* ctx, const GemmArgs& g, int mt, int nt, int batc
                 c.neg_cnt = g.neg_cnt + k0 / kTile;
                 c.neg_idx = g.neg_idx + k0;
             }
-            LAUNCH(launch_gemm_ozaki(c, mt, nt, S, ctx->oz_ws.p, ctx->oz_ws.cap, ctx->oz_err.as<int>(), ctx->cur));
+            const bool reuse = same_a && g.K <= kOzakiMaxK && ctx->oz_last.A == c.A && ctx->oz_last.lda == c.lda &&
+                               ctx->oz_last.mt == mt && ctx->oz_last.K == c.K && ctx->oz_last.S == S;
+            LAUNCH(launch_gemm_ozaki(c, mt, nt, S, ctx->oz_ws.p, ctx->oz_ws.cap, ctx->oz_err.as<int>(), ctx->cur, reuse));
+            ctx->oz_last.A = c.A;
+            ctx->oz_last.lda = c.lda;
+            ctx->oz_last.mt = mt;
+            ctx->oz_last.K = c.K;
+            ctx->oz_last.S = S;
             ctx->launches += 4;   // two row-maximum and two slicing kernels ride along
             ctx->stats.tc_gemm_launches++;
         }
@@ -1016,10 +1030,15 @@ bool nccl_load(std::string& err) {
 int ensure_panel_plan(cheq_ctx* ctx, const Layout& L) {
     const int nxt = (L.scf ? L.nxp : L.NP) / kTile, nht = (L.scf ? L.nhp : 0) / kTile;
     PanelPlan& pp = ctx->pplan;
-    if (pp.nxt == nxt && pp.nht == nht && pp.tpp == ctx->tiles_per_panel && pp.world == ctx->world &&
-        pp.rank == ctx->rank)
+    // With the trailing updates on the tcgen05 path, 8-tile panels (K = 1024) feed it better than 4-tile ones (S20k
+    // panel schedule on one GPU: 0.199 s with 4, 0.186 s with 8, 0.205 s with 16) -- as long as every rank still owns
+    // at least four panels, otherwise the owner-computes updates go out of balance.
+    int tpp = ctx->tiles_per_panel;
+    if (!ctx->tiles_per_panel_set && ctx->ozaki_slices > 0 && (long)(nxt + nht) >= 32l * ctx->world) tpp = 8;
+    ctx->tpp_now = tpp;
+    if (pp.nxt == nxt && pp.nht == nht && pp.tpp == tpp && pp.world == ctx->world && pp.rank == ctx->rank)
         return CHEQ_OK;
-    pp.build(nxt, nht, ctx->tiles_per_panel, ctx->world, ctx->rank);
+    pp.build(nxt, nht, tpp, ctx->world, ctx->rank);
     CU(ctx->own_list.ensure(std::max<size_t>(4, pp.own_tiles.size() * sizeof(int))));
     CU(ctx->col_mask.ensure(std::max<size_t>(4, pp.mask.size())));
     CU(cudaStreamSynchronize(ctx->stream));   // earlier kernels may still read the previous plan's arrays
@@ -1303,7 +1322,9 @@ int factor_blocked(Dense& D, int p_begin, int p_end) {
             if (rc) return rc;
             CU(cudaEventRecord(ctx->ev_ready, ms));
         }
+        ctx->oz_same_a = head > 0;   // the panel's rows were sliced for the head update already
         const int rc = update_columns(D, j0, n, e, d_list + pos + head, pp.own_tiles.data() + pos + head, cnt - head);
+        ctx->oz_same_a = false;
         if (rc) return rc;
     }
     if (ctx->world > 1 && ctx->push_now && ctx->push_dma) {
@@ -2090,7 +2111,7 @@ int factor_and_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
         const bool want_push = ctx->p2p_mode >= 2 || (ctx->p2p_mode == 1 && (ctx->world <= 4 || (long)L.NP >= 49152));
         ctx->push_now = ctx->links.enabled && want_push;
         ctx->push_dma = ctx->push_now && ctx->p2p_mode != 2;
-        if (!ctx->push_now) CU(ctx->stage.ensure((size_t)L.MT * ctx->tiles_per_panel * kTile * 8));
+        if (!ctx->push_now) CU(ctx->stage.ensure((size_t)L.MT * ctx->tpp_now * kTile * 8));
     }
     const uint8_t* mask_h = dist ? ctx->col_mask.as<uint8_t>() + L.nxp / kTile : nullptr;
 
@@ -2921,7 +2942,10 @@ int32_t cheq_ctx_create(int32_t device, cheq_ctx** out) {
     if (const char* env = getenv("CHEQ_KRYLOV_FORCE_IT")) ctx->krylov_force_it = std::max(2, atoi(env));
     if (const char* env = getenv("CHEQ_PANEL_FLAT")) ctx->panel_flat = atoi(env) != 0;
     if (const char* env = getenv("CHEQ_FACTOR_MODE")) ctx->factor_mode = std::max(0, std::min(2, atoi(env)));
-    if (const char* env = getenv("CHEQ_TILES_PER_PANEL")) ctx->tiles_per_panel = std::max(1, std::min(64, atoi(env)));
+    if (const char* env = getenv("CHEQ_TILES_PER_PANEL")) {
+        ctx->tiles_per_panel = std::max(1, std::min(64, atoi(env)));
+        ctx->tiles_per_panel_set = true;
+    }
     *out = ctx;
     return CHEQ_OK;
 }
@@ -3096,7 +3120,10 @@ int32_t cheq_set_factor_mode(cheq_ctx* ctx, int32_t mode, int32_t tiles_per_pane
     if (!ctx || mode < 0 || mode > 2 || tiles_per_panel < 0 || tiles_per_panel > 64) return CHEQ_ERR_INVALID_ARGUMENT;
     std::lock_guard<std::mutex> lock(ctx->mu);
     ctx->factor_mode = mode;
-    if (tiles_per_panel > 0) ctx->tiles_per_panel = tiles_per_panel;
+    if (tiles_per_panel > 0) {
+        ctx->tiles_per_panel = tiles_per_panel;
+        ctx->tiles_per_panel_set = true;
+    }
     return CHEQ_OK;
 }
 

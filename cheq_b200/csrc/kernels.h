@@ -134,7 +134,7 @@ size_t ozaki_workspace_bytes(int slices, int m_tiles, int n_tiles, int K);
 bool ozaki_supported(int slices, int K);
 cudaError_t configure_ozaki_kernels();
 cudaError_t launch_gemm_ozaki(const GemmArgs& g, int m_tiles, int n_tiles, int slices, void* ws, size_t ws_bytes,
-                              int* error, cudaStream_t stream);
+                              int* error, cudaStream_t stream, bool reuse_a = false);
 cudaError_t launch_dmma_rate(double* out, int blocks, int threads, int iters, cudaStream_t stream);
 cudaError_t launch_latency_probe(double* out, long long* cycles, int iters, cudaStream_t stream);
 cudaError_t launch_dfma_rate(double* out, int blocks, int iters, cudaStream_t stream);

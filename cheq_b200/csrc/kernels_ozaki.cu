@@ -119,6 +119,7 @@ struct OzGemmArgs {
     int nkb;               // K / 32
     int m_tiles, n_tiles;  // 128-row and 64-column tiles
     int lower, row0, subtract;
+    const int* n_list;     // nullable: 128-column tile t of the grid is tile column n_list[t] of C (B is gathered by the slicer)
     const ScfState* state; // nullable
     int* error;            // device flag: != 0 -> the grid drains without touching C
 };
@@ -137,7 +138,9 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
         tile_m = first + in % gsz;
         tile_n = in / gsz;
     }
-    if (a.lower && a.row0 + tile_m * kOzTM + kOzTM - 1 < tile_n * kOzTN) return;   // entirely above the diagonal
+    // first column of this tile in C (column-list mode: the owned tile columns of a rank, any ascending set)
+    const long ccol0 = (a.n_list ? (long)a.n_list[tile_n >> 1] * kTile : (long)(tile_n >> 1) * kTile) + (tile_n & 1) * kOzTN;
+    if (a.lower && a.row0 + tile_m * kOzTM + kOzTM - 1 < ccol0) return;   // entirely above the diagonal
     if (a.state && !a.state[0].active) return;
     if (*(volatile int*)a.error != 0) return;
 
@@ -171,7 +174,7 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
     // Every thread owns one row of the C tile.  Its 64 old values are fetched NOW, so that their latency hides behind
     // the main loop instead of sitting in the epilogue (which no other CTA on this SM can overlap: TMEM is full).
     const long row = (long)tile_m * kOzTM + t;
-    double* crow = a.C + row + (long)tile_n * kOzTN * a.ldc;
+    double* crow = a.C + row + ccol0 * a.ldc;
     double cold[kOzTN];
     if (a.subtract) {
 #pragma unroll
@@ -251,11 +254,14 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
 
 // ---- slicing ---------------------------------------------------------------------------------------------------
 // largest magnitude per row (bit pattern of a non-negative double orders like the integer): grid (rows / 128, K chunks)
+// tile_list (nullable): 128-row block b of the output is row tile tile_list[b] of X
 __global__ void __launch_bounds__(128) oz_rowmax_kernel(const double* __restrict__ X, long ld, int K, int kchunk,
-                                                        unsigned long long* __restrict__ mx) {
+                                                        unsigned long long* __restrict__ mx,
+                                                        const int* __restrict__ tile_list) {
     const long r = (long)blockIdx.x * 128 + threadIdx.x;
+    const long rsrc = (tile_list ? (long)tile_list[blockIdx.x] : (long)blockIdx.x) * 128 + threadIdx.x;
     const int k0 = blockIdx.y * kchunk, k1 = min(K, k0 + kchunk);
-    const double* p = X + r + (long)k0 * ld;
+    const double* p = X + rsrc + (long)k0 * ld;
     double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
     int k = k0;
     for (; k + 4 <= k1; k += 4, p += 4 * ld) {
@@ -283,7 +289,8 @@ template <int S, int RB>
 __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ X, long ld, int K,
                                                        const unsigned long long* __restrict__ mx,
                                                        double* __restrict__ scale_out, int8_t* __restrict__ planes,
-                                                       const int* __restrict__ neg_cnt, const int* __restrict__ neg_idx) {
+                                                       const int* __restrict__ neg_cnt, const int* __restrict__ neg_idx,
+                                                       const int* __restrict__ tile_list) {
     constexpr int B = 8 * S - 2;
     __shared__ unsigned char neg[128];
     const int t = threadIdx.x;
@@ -299,11 +306,12 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
 #pragma unroll 1
     for (int i = t; i < kItems; i += 256) {
         const int r = i % RB, c16 = i / RB;          // c16: 16-column chunk of the K tile, 0..7
-        const long row = (long)rb * RB + r;
+        const long row = (long)rb * RB + r;   // row of the sliced operand; its source row in X differs in list mode
+        const long rsrc = tile_list ? (long)tile_list[row >> 7] * 128 + (row & 127) : row;
         const int e = oz_exponent(mx[row]);
         if (kt == 0 && c16 == 0) scale_out[row] = ldexp(1.0, e - 6);
         const double sc = ldexp(1.0, B - e);
-        const double* src = X + row + ((long)kt * 128 + c16 * 16) * ld;
+        const double* src = X + rsrc + ((long)kt * 128 + c16 * 16) * ld;
         long long v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
@@ -333,31 +341,50 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
     }
 }
 
+// workspace: [row maxima of A | scales of A | planes of A] [row maxima of B | scales of B | planes of B]; the A part
+// depends on (m, K, S) only, so a following call with the same A can reuse it
+struct OzLayout {
+    size_t mxa, sa, pa, mxb, sb, pb, bytes;
+    OzLayout(int S, size_t m, size_t n, size_t K) {
+        auto up = [](size_t v) { return (v + 1023) / 1024 * 1024; };
+        mxa = 0;
+        sa = mxa + m * 8;
+        pa = up(sa + m * 8);
+        mxb = up(pa + (size_t)S * m * K);
+        sb = mxb + n * 8;
+        pb = up(sb + n * 8);
+        bytes = pb + (size_t)S * n * K;
+    }
+};
+
 template <int S>
 cudaError_t oz_launch_t(const GemmArgs& g, int m_tiles, int n_tiles, void* ws, size_t ws_bytes, int* error,
-                        cudaStream_t stream) {
+                        bool reuse_a, cudaStream_t stream) {
     const long m = (long)m_tiles * kTile, n = (long)n_tiles * kTile;
     const int K = g.K, nkb = K / kOzKB;
-    // workspace carve-up
+    const OzLayout L(S, (size_t)m, (size_t)n, (size_t)K);
+    if (L.bytes > ws_bytes) return cudaErrorInvalidValue;
     char* w = (char*)ws;
-    unsigned long long* mxa = (unsigned long long*)w;
-    unsigned long long* mxb = mxa + m;
-    double* sa = (double*)(mxb + n);
-    double* sb = sa + m;
-    size_t off = (size_t)(2 * (m + n)) * 8;
-    off = (off + 1023) / 1024 * 1024;
-    int8_t* PA = (int8_t*)(w + off);
-    int8_t* PB = PA + (size_t)S * m * K;
-    if (off + (size_t)S * (m + n) * K > ws_bytes) return cudaErrorInvalidValue;
-    cudaError_t e = cudaMemsetAsync(mxa, 0, (size_t)(m + n) * 8, stream);
-    if (e != cudaSuccess) return e;
+    unsigned long long* mxa = (unsigned long long*)(w + L.mxa);
+    unsigned long long* mxb = (unsigned long long*)(w + L.mxb);
+    double* sa = (double*)(w + L.sa);
+    double* sb = (double*)(w + L.sb);
+    int8_t* PA = (int8_t*)(w + L.pa);
+    int8_t* PB = (int8_t*)(w + L.pb);
     const int kchunk = 128, ksplit = (K + kchunk - 1) / kchunk;
-    oz_rowmax_kernel<<<dim3((unsigned)(m / 128), ksplit), 128, 0, stream>>>(g.A, g.lda, K, kchunk, mxa);
-    oz_rowmax_kernel<<<dim3((unsigned)(n / 128), ksplit), 128, 0, stream>>>(g.B, g.ldb, K, kchunk, mxb);
-    oz_slice_kernel<S, kOzTM><<<dim3((unsigned)(m / kOzTM), K / 128), 256, 0, stream>>>(g.A, g.lda, K, mxa, sa, PA,
-                                                                                       nullptr, nullptr);
+    cudaError_t e;
+    if (!reuse_a) {
+        e = cudaMemsetAsync(mxa, 0, (size_t)m * 8, stream);
+        if (e != cudaSuccess) return e;
+        oz_rowmax_kernel<<<dim3((unsigned)(m / 128), ksplit), 128, 0, stream>>>(g.A, g.lda, K, kchunk, mxa, nullptr);
+        oz_slice_kernel<S, kOzTM><<<dim3((unsigned)(m / kOzTM), K / 128), 256, 0, stream>>>(g.A, g.lda, K, mxa, sa, PA,
+                                                                                           nullptr, nullptr, nullptr);
+    }
+    e = cudaMemsetAsync(mxb, 0, (size_t)n * 8, stream);
+    if (e != cudaSuccess) return e;
+    oz_rowmax_kernel<<<dim3((unsigned)(n / 128), ksplit), 128, 0, stream>>>(g.B, g.ldb, K, kchunk, mxb, g.n_list);
     oz_slice_kernel<S, kOzTN><<<dim3((unsigned)(n / kOzTN), K / 128), 256, 0, stream>>>(g.B, g.ldb, K, mxb, sb, PB,
-                                                                                       g.neg_cnt, g.neg_idx);
+                                                                                       g.neg_cnt, g.neg_idx, g.n_list);
     OzGemmArgs a{};
     a.PA = PA;
     a.PB = PB;
@@ -371,6 +398,7 @@ cudaError_t oz_launch_t(const GemmArgs& g, int m_tiles, int n_tiles, void* ws, s
     a.lower = g.lower;
     a.row0 = g.row0;
     a.subtract = g.subtract;
+    a.n_list = g.n_list;
     a.state = g.state;
     a.error = error;
     constexpr int smem = oz_stages(S) * S * (kOzPlaneA + kOzPlaneB);
@@ -381,10 +409,7 @@ cudaError_t oz_launch_t(const GemmArgs& g, int m_tiles, int n_tiles, void* ws, s
 }  // namespace
 
 size_t ozaki_workspace_bytes(int slices, int m_tiles, int n_tiles, int K) {
-    const size_t m = (size_t)m_tiles * kTile, n = (size_t)n_tiles * kTile;
-    size_t off = 2 * (m + n) * 8;
-    off = (off + 1023) / 1024 * 1024;
-    return off + (size_t)slices * (m + n) * (size_t)K;
+    return OzLayout(slices, (size_t)m_tiles * kTile, (size_t)n_tiles * kTile, (size_t)K).bytes;
 }
 
 bool ozaki_supported(int slices, int K) {
@@ -403,17 +428,19 @@ cudaError_t configure_ozaki_kernels() {
     return e;
 }
 
-// C (-)= A S B^T through int8 slices; single frame, no column list, no peers.  `error`: device int, raised by a
+// C (-)= A S B^T through int8 slices; single frame, no peers.  Column-list mode as in gemm_nt_kernel: tile column t of
+// the grid is tile column n_list[t] of C and of B (both then point at absolute tile column 0).  `error`: device int, raised by a
 // pipeline timeout (the caller checks it at its next synchronisation point).
+// reuse_a: the previous call on this workspace sliced the same A (pointer, rows, K, slices): keep its planes.
 cudaError_t launch_gemm_ozaki(const GemmArgs& g, int m_tiles, int n_tiles, int slices, void* ws, size_t ws_bytes,
-                              int* error, cudaStream_t stream) {
-    if (!ozaki_supported(slices, g.K) || g.n_list || g.n_peers) return cudaErrorInvalidValue;
+                              int* error, cudaStream_t stream, bool reuse_a) {
+    if (!ozaki_supported(slices, g.K) || g.n_peers) return cudaErrorInvalidValue;
     switch (slices) {
-        case 4: return oz_launch_t<4>(g, m_tiles, n_tiles, ws, ws_bytes, error, stream);
-        case 5: return oz_launch_t<5>(g, m_tiles, n_tiles, ws, ws_bytes, error, stream);
-        case 6: return oz_launch_t<6>(g, m_tiles, n_tiles, ws, ws_bytes, error, stream);
-        case 7: return oz_launch_t<7>(g, m_tiles, n_tiles, ws, ws_bytes, error, stream);
-        case 8: return oz_launch_t<8>(g, m_tiles, n_tiles, ws, ws_bytes, error, stream);
+        case 4: return oz_launch_t<4>(g, m_tiles, n_tiles, ws, ws_bytes, error, reuse_a, stream);
+        case 5: return oz_launch_t<5>(g, m_tiles, n_tiles, ws, ws_bytes, error, reuse_a, stream);
+        case 6: return oz_launch_t<6>(g, m_tiles, n_tiles, ws, ws_bytes, error, reuse_a, stream);
+        case 7: return oz_launch_t<7>(g, m_tiles, n_tiles, ws, ws_bytes, error, reuse_a, stream);
+        case 8: return oz_launch_t<8>(g, m_tiles, n_tiles, ws, ws_bytes, error, reuse_a, stream);
     }
     return cudaErrorInvalidValue;
 }

@@ -145,14 +145,11 @@ static double run_case(const Case& c, int* d_err) {
         OzGemmArgs a{};
         {
             char* w = (char*)ws;
-            unsigned long long* mxa = (unsigned long long*)w;
-            double* sa = (double*)(mxa + m + n);
-            size_t off = (size_t)(2 * (m + n)) * 8;
-            off = (off + 1023) / 1024 * 1024;
-            a.PA = (int8_t*)(w + off);
-            a.PB = a.PA + (size_t)c.S * m * K;
-            a.sa = sa;
-            a.sb = sa + m;
+            const OzLayout L(c.S, (size_t)m, (size_t)n, (size_t)K);
+            a.PA = (int8_t*)(w + L.pa);
+            a.PB = (int8_t*)(w + L.pb);
+            a.sa = (double*)(w + L.sa);
+            a.sb = (double*)(w + L.sb);
             a.C = dC;
             a.ldc = ldc;
             a.nkb = K / 32;
@@ -200,6 +197,98 @@ static double run_case(const Case& c, int* d_err) {
     return ok ? 0.0 : 1.0;
 }
 
+// Column-list mode as the multi-GPU trailing update uses it: C and B are addressed from absolute tile column 0, the grid
+// covers the tile columns in `list`; the update is issued as head + rest with the planes of A reused by the second call.
+static double run_list_case(int S, int* d_err) {
+    const int NTa = 12, e = 3, K = 512;
+    const int m_tiles = NTa - e + 1;                 // rows from tile e down, plus one tile of right-hand-side rows
+    const long m = (long)m_tiles * 128, nabs = (long)NTa * 128;
+    const long lda = m, ldb = nabs + 128, ldc = m + 128;
+    std::vector<int> list = {4, 6, 7, 10};
+    unsigned long long sm = 77 + S;
+    auto uni = [&]() {
+        unsigned long long z = (sm += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        return (double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+    };
+    std::vector<double> A((size_t)lda * K), B((size_t)ldb * K), C((size_t)ldc * nabs), C0;
+    for (auto& v : A) v = uni();
+    for (auto& v : B) v = 3.0 * uni();
+    for (auto& v : C) v = uni();
+    C0 = C;
+    std::vector<int> neg_cnt(K / 128, 0), neg_idx(K, 0);
+    std::vector<double> sgn(K, 1.0);
+    for (int k = 0; k < K; ++k)
+        if ((k * 7) % 5 == 0) {
+            sgn[k] = -1.0;
+            neg_idx[(k / 128) * 128 + neg_cnt[k / 128]++] = k % 128;
+        }
+    double *dA, *dB, *dC;
+    int *dcnt, *didx, *dlist;
+    void* ws;
+    const size_t wsb = ozaki_workspace_bytes(S, m_tiles, (int)list.size(), K);
+    CK(cudaMalloc(&dA, A.size() * 8));
+    CK(cudaMalloc(&dB, B.size() * 8));
+    CK(cudaMalloc(&dC, C.size() * 8));
+    CK(cudaMalloc(&dcnt, neg_cnt.size() * 4));
+    CK(cudaMalloc(&didx, neg_idx.size() * 4));
+    CK(cudaMalloc(&dlist, list.size() * 4));
+    CK(cudaMalloc(&ws, wsb));
+    CK(cudaMemcpy(dA, A.data(), A.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, B.data(), B.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dC, C.data(), C.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dcnt, neg_cnt.data(), neg_cnt.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(didx, neg_idx.data(), neg_idx.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dlist, list.data(), list.size() * 4, cudaMemcpyHostToDevice));
+    GemmArgs g{};
+    g.A = dA;
+    g.B = dB;
+    g.C = dC;
+    g.lda = lda;
+    g.ldb = ldb;
+    g.ldc = ldc;
+    g.K = K;
+    g.lower = 1;
+    g.subtract = 1;
+    g.neg_cnt = dcnt;
+    g.neg_idx = didx;
+    g.row0 = e * 128;
+    g.n_list = dlist;
+    CK(launch_gemm_ozaki(g, m_tiles, 1, S, ws, wsb, d_err, 0, false));          // head: the first listed column
+    g.n_list = dlist + 1;
+    CK(launch_gemm_ozaki(g, m_tiles, (int)list.size() - 1, S, ws, wsb, d_err, 0, true));   // rest, planes of A reused
+    CK(cudaDeviceSynchronize());
+    int err = 0;
+    CK(cudaMemcpy(&err, d_err, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(C.data(), dC, C.size() * 8, cudaMemcpyDeviceToHost));
+    double worst = 0.0, untouched = 0.0;
+    for (long j = 0; j < nabs; ++j) {
+        const bool listed = std::find(list.begin(), list.end(), (int)(j / 128)) != list.end();
+        for (long i = 0; i < m; i += 3) {
+            const double c0 = C0[i + j * ldc], got = C[i + j * ldc];
+            const bool skipped = !listed || (e * 128 + (i / 128) * 128 + 127 < (j / 64) * 64);
+            if (skipped) {
+                untouched = std::max(untouched, std::fabs(got - c0));
+                continue;
+            }
+            long double ref = 0.0L;
+            for (long k = 0; k < K; ++k) ref += (long double)A[i + k * lda] * (long double)(sgn[k] * B[j + k * ldb]);
+            worst = std::max(worst, (double)fabsl((long double)got - ((long double)c0 - ref)) / (3.0 * K));
+        }
+    }
+    const double bound = std::max(std::ldexp(1.0, -(8 * S - 6)), 4e-16);
+    const bool ok = err == 0 && worst <= bound && untouched == 0.0;
+    printf("{\"case\": \"column list {4, 6, 7, 10} of 12, rows from tile 3, K 512, S %d, head + rest with reused A planes\", "
+           "\"pipeline_error\": %d, \"max_err_over_rowmax_colmax_K\": %.3e, \"untouched_diff\": %.1e, \"ok\": %s}\n",
+           S, err, worst, untouched, ok ? "true" : "false");
+    fflush(stdout);
+    cudaFree(dA); cudaFree(dB); cudaFree(dC); cudaFree(dcnt); cudaFree(didx); cudaFree(dlist); cudaFree(ws);
+    if (err) CK(cudaMemset(d_err, 0, 4));
+    return ok ? 0.0 : 1.0;
+}
+
 int main(int argc, char** argv) {
     const bool quick = argc > 1 && !strcmp(argv[1], "quick");
     CK(configure_ozaki_kernels());
@@ -212,6 +301,8 @@ int main(int argc, char** argv) {
     fails += run_case({1, 1, 1024, 7, 0, 0, 400, false}, d_err);
     for (int S = 4; S <= 8; ++S) fails += run_case({3, 2, 640, S, 0, 1, 600, false}, d_err);
     fails += run_case({5, 3, 1152, 7, 1, 1, 1500, false}, d_err);
+    fails += run_list_case(7, d_err);
+    fails += run_list_case(5, d_err);
     fails += run_case({20, 20, 2048, 7, 1, 1, 1500, !quick}, d_err);
     if (!quick) {
         fails += run_case({64, 64, 4096, 7, 0, 1, 300, true}, d_err);
