@@ -291,7 +291,7 @@ class ClockSampler:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
-        sm, smax, reasons = [], [], set()
+        sm, smax, power, reasons = [], [], [], set()
         for ln in self.lines:
             f = [c.strip() for c in ln.split(",")]
             if len(f) < 9:
@@ -299,13 +299,15 @@ class ClockSampler:
             try:
                 sm.append(float(f[1]))
                 smax.append(float(f[2]))
+                power.append(float(f[3]))
             except ValueError:
                 continue
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "sm_mhz_min": min(sm) if sm else None,
+                "power_w_max": max(power) if power else None}
 
 
 def measure_fp64_peak(torch, device):
@@ -636,7 +638,11 @@ def run_ours(args, rank, local_rank, world):
     lib.cheq_set_profiling(ctx.handle, 0)
     for _ in range(min(args.warmup, 1)):
         step_host()
+    sampler_e2e = ClockSampler(local_rank)
+    if rank == 0:
+        sampler_e2e.start()
     ms_e2e = timed(step_host, args.steps)
+    clocks_e2e = sampler_e2e.stop() if rank == 0 else None
     stats_e2e = ctx.stats()
     assert abs(pot.value - mu_dev) < 1e-9 and np.max(np.abs(h_q.numpy() - q_dev)) < 1e-9
 
@@ -751,6 +757,7 @@ def run_ours(args, rank, local_rank, world):
                               "peak_source": "MEASURED_PEAKS.json hbm_gbs"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * (24 + 8 + 8 + 8 + 1)),
                 "d2h_bytes_per_step": int(n * 8 + 64),
+                "clocks": clocks_e2e,
                 "phases_ms_last_step": {k: stats_e2e[k] for k in ("ms_total", "ms_host_prepare", "ms_h2d", "ms_assemble",
                                                                   "ms_factor_once", "ms_scf", "ms_d2h")}},
         "gpu_launches": int(launches_t.item()),
@@ -761,7 +768,12 @@ def run_ours(args, rank, local_rank, world):
         line["dist_check"] = dist_check
     if secondary is not None:
         line["secondary"] = secondary
-    if full is not None:
+    if full is not None and os.environ.get("CHEQ_ORACLE_CACHE"):
+        # development runs: the parity reference was pre-computed elsewhere (tools/dev_cache), so its CPU time says
+        # nothing about this box
+        line["cpu_baseline"] = None
+        line["parity"]["reference"] += "; loaded from CHEQ_ORACLE_CACHE (pre-computed, CPU time not measured in this run)"
+    elif full is not None:
         line["cpu_baseline"] = {"value": float(full["t_total"]), "unit": UNIT, "cores": int(full["cores"]), "kind": "port",
                                 "sample": f"the whole workload: ONE complete CPU solve of {name} ({int(full['iterations'])} SCF "
                                           f"iterations, assembly {float(full['t_asm']):.1f} s, median LU "
