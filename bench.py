@@ -7,9 +7,13 @@ assembly of the shielded-Coulomb matrix, factorisation, the complete hydrogen SC
   value      seconds per solve with the per-atom inputs already resident in HBM (cheq_solve_device)
   e2e        the same through the public API with host (pinned) buffers: H2D of the inputs and D2H of the charges
              inside the timed region (cheq_solve)
-  roofline   the dominant kernel (gemm_nt_kernel, FP64 DMMA): algorithmic flops / summed launch durations, both
-             measured live with CUDA events on the engine's stream; peak = cuBLAS DGEMM measured in the same run
-             (MEASURED_PEAKS.json has no fp64 entry).  `roofline_matvec` is the HBM-bound kernel of the stale-factor
+  roofline   the dominant kernel, measured live with CUDA events around every launch on the engine's stream (second pass):
+             oz_gemm_kernel (the deep FP64 updates as int8 slice products on tcgen05): int8 tensor operations executed /
+             summed launch durations incl. the slicing passes, against the int8 tensor peak (2 x MEASURED_PEAKS.json's
+             bf16 figure, or the higher int8 issue rate measured by tools/tc05_probe); its FP64-equivalent rate is
+             reported beside it.  `roofline_other_gemm` is gemm_nt_kernel (FP64 DMMA: the shallow updates) against cuBLAS
+             DGEMM measured in the same run (MEASURED_PEAKS.json has no fp64 entry); with the tcgen05 path off it is the
+             dominant kernel and takes the `roofline` slot.  `roofline_matvec` is the HBM-bound kernel of the stale-factor
              SCF iterations (tile_matvec_kernel), `roofline_assembly` the assembly kernel.
   parity     the timed result against ONE real full solve of the same workload by the CPU oracle (the reference's
              algorithm as written; cached under /tmp, computed by the reference arm or, if absent, here)

@@ -268,7 +268,7 @@ struct cheq_ctx {
     // device workspace (grow-only)
     DeviceBuffer in_xyz, in_chi, in_hard, in_radius, in_nq, perm, type, x, y, z, diag, chi, hard, vext, A, S0,
         Linv, v, q, scratch, counters, state, active, blob, pc_xyz, pc_q, pc_type, out_q, misc0, misc1, misc2,
-        lu_f, lu_piv, sgn, sgn_flags, xsol;
+        lu_f, lu_ut, lu_piv, sgn, sgn_flags, xsol;
     // stale-factor SCF iterations (kernels_krylov.cu): explicit R = L_hh^-T S of the frozen hydrogen factor, partial
     // sums of the tiled matrix-vector products, the small vectors of GMRES, device / pinned-host scalars
     DeviceBuffer kr_R, kr_Rf, kr_S0t, kr_tb, kr_part, kr_vec, kr_sc, kr_wx, kx_local;
@@ -293,6 +293,7 @@ struct cheq_ctx {
                                       // fp32 afterwards: 38 bits are plenty); 0 = as CHEQ_OZAKI
     int ozaki_min_k = 512;            // CHEQ_OZAKI_MIN_K: shallower updates stay on DMMA (slicing + epilogue do not amortise;
                                       // S20k: 0.1957 / 0.1909 / 0.1961 s with 1024 / 512 / 256)
+    int force_lu = 0;                 // CHEQ_FORCE_LU=1: single-frame solves take the pivoted-LU path (timing / test knob)
     int ozaki_now = 0;                // slices in force for the launches being issued
     bool oz_same_a = false;           // set by a caller whose next update multiplies the SAME left operand as its previous one
     struct { const double* A = nullptr; long lda = 0; int mt = 0, K = 0, S = 0; } oz_last;   // A operand whose planes are in oz_ws
@@ -2396,7 +2397,8 @@ int lu_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
     const cheq_options& o = *io.opt;
     cudaStream_t st = ctx->stream;
     const int n1p = lu_padded_size(L.NP);
-    CU(ctx->lu_f.ensure((size_t)n1p * (n1p + 1) * 8));
+    CU(ctx->lu_f.ensure(lu_matrix_bytes(L.NP)));
+    CU(ctx->lu_ut.ensure(lu_workspace_bytes(L.NP)));
     CU(ctx->lu_piv.ensure((size_t)n1p * sizeof(int)));
     ScfState* state = ctx->state.as<ScfState>();
     double damping0 = 1.0;
@@ -2408,7 +2410,8 @@ int lu_scf(cheq_ctx* ctx, const SolveIO& io, Prepared& P) {
     unsigned long long launches = 0;
     const uint32_t max_it = L.scf ? o.max_iterations : 1;
     for (uint32_t it = 1; it <= max_it; ++it) {
-        CU(launch_lu_solve(ctx->A.as<double>(), L.ld, L.NP, L.nxp, L.scf ? 1 : 0, ctx->lu_f.as<double>(), q,
+        CU(launch_lu_solve(ctx->A.as<double>(), L.ld, L.NP, L.nxp, L.scf ? 1 : 0, ctx->lu_f.as<double>(),
+                           ctx->lu_ut.as<double>(), q,
                            ctx->hard.as<double>(), ctx->type.as<uint8_t>(), io.total_charge,
                            ctx->lu_piv.as<int>(), v, state, &launches, st));
         LAUNCH(launch_scf_mix(v, q, L.NP, ctx->type.as<uint8_t>(), L.NP, state, 1, st));
@@ -2804,6 +2807,7 @@ int solve_impl(cheq_ctx* ctx, const SolveIO& io) {
         std::vector<int> not_spd;
         for (int f = 0; f < batch; ++f)
             if (ctx->h_state[f].info != 0) not_spd.push_back(f);
+        if (ctx->force_lu && batch == 1 && not_spd.empty()) not_spd.push_back(0);
         if (batch == 1 && !not_spd.empty()) {
             // single solve: redo with the pivoted LU
             rc = prepare_and_assemble(ctx, io, f0, 1, io.opt->hydrogen_scf != 0, P, true, true);
@@ -2916,6 +2920,7 @@ int32_t cheq_ctx_create(int32_t device, cheq_ctx** out) {
         cheq_ctx_destroy(ctx);
         return CHEQ_ERR_CUDA;
     }
+    if (const char* env = getenv("CHEQ_FORCE_LU")) ctx->force_lu = atoi(env) != 0;
     if (const char* env = getenv("CHEQ_OZAKI")) ctx->ozaki_slices = atoi(env);
     if (const char* env = getenv("CHEQ_OZAKI_R")) ctx->ozaki_slices_r = atoi(env);
     if (const char* env = getenv("CHEQ_OZAKI_MIN_K")) ctx->ozaki_min_k = std::max(128, atoi(env));
@@ -2982,7 +2987,7 @@ void cheq_ctx_destroy(cheq_ctx* ctx) {
                             &ctx->type, &ctx->x, &ctx->y, &ctx->z, &ctx->diag, &ctx->chi, &ctx->hard, &ctx->vext,
                             &ctx->A, &ctx->S0, &ctx->Linv, &ctx->v, &ctx->q, &ctx->scratch, &ctx->counters,
                             &ctx->state, &ctx->active, &ctx->blob, &ctx->pc_xyz, &ctx->pc_q, &ctx->pc_type,
-                            &ctx->out_q, &ctx->misc0, &ctx->misc1, &ctx->misc2, &ctx->lu_f, &ctx->lu_piv, &ctx->sgn, &ctx->sgn_flags, &ctx->xsol};
+                            &ctx->out_q, &ctx->misc0, &ctx->misc1, &ctx->misc2, &ctx->lu_f, &ctx->lu_ut, &ctx->lu_piv, &ctx->sgn, &ctx->sgn_flags, &ctx->xsol};
     for (DeviceBuffer* b : bufs) b->release();
     if (ctx->mf) {
         ctx->mf->release();

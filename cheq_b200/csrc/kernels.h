@@ -281,9 +281,12 @@ cudaError_t launch_matfree_unpack(const double* sol, int NP, double* x, ScfState
 
 // ---- LU fallback (kernels_lu.cu) ------------------------------------------------------------------------------
 int lu_padded_size(int NP);
+size_t lu_matrix_bytes(int NP);      // F: (NP + 128) x (NP + 256) doubles
+size_t lu_workspace_bytes(int NP);   // Ut: transposed U12 of one outer block
 // Builds the bordered matrix from the assembled lower triangle (A is left untouched), factors it with partial
-// pivoting, solves, and writes x (internal order) to v and the border unknown to state[0].mu.
-cudaError_t launch_lu_solve(const double* A, long ld, int NP, int nxp, int scf, double* F, const double* q,
+// pivoting (32-column panels inside 128-column outer blocks, the update right of an outer block on the FP64 tensor
+// cores), solves, and writes x (internal order) to v and the border unknown to state[0].mu.
+cudaError_t launch_lu_solve(const double* A, long ld, int NP, int nxp, int scf, double* F, double* Ut, const double* q,
                             const double* hard, const uint8_t* type, double total_charge, int* ipiv, double* v,
                             ScfState* state, unsigned long long* launches, cudaStream_t stream);
 

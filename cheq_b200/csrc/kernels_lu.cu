@@ -5,7 +5,9 @@
 // geometries but not for every input the reference accepts (its own C2H4 fixture, tests/hydrogen.rs:175-207,
 // has two hydrogens 0.21 Angstrom apart and an indefinite matrix).  When the Cholesky meets a non-positive pivot the
 // engine re-solves with this blocked right-looking LU of [[A, 1], [1^T, 0]] with the right-hand side carried as
-// an extra column.  It is a correctness path: plain FP64 FMA tiles, no tensor cores.
+// an extra column.  Two-level blocking: 32-column panels (pivot search, row interchanges, eager updates) inside outer
+// blocks of 128 columns; everything right of an outer block is updated once per block with K = 128 on the FP64 tensor
+// cores (gemm_nt_kernel, DMMA) from a transposed copy of U12 -- the bulk of the (2/3) N^3 flops.
 #include <cuda_runtime.h>
 
 #include "device_types.h"
@@ -14,9 +16,11 @@
 namespace cheq {
 namespace {
 
-constexpr int NB = 32;   // LU block size
+constexpr int NB = 32;    // panel width
+constexpr int OB = 128;   // outer block: delayed (tensor-core) update of everything right of it
 
-// F (n1p x (n1p + 1), ld n1p) <- bordered matrix in internal order.  n1p = NP + 64.
+// F (n1p x (n1p + 128), ld n1p) <- bordered matrix in internal order.  n1p = NP + 128; column n1p is the right-hand side,
+// the 127 columns after it are zero padding (the tensor-core update works on whole 128-column tiles).
 //   F[i, j] = A[max, min] (i, j < NP);  F[i, NP] = F[NP, i] = one_i;  F[NP, NP] = 0;  identity padding beyond;
 //   hydrogen diagonal: hardness * (1 + clamp(q) * factor) (implementation.rs:567-572);
 //   column n1p = right-hand side: c_i (row NP of the trapezoid's rhs rows), total charge at row NP.
@@ -40,7 +44,7 @@ __global__ void lu_build_kernel(const double* A, long ld, int NP, int n1p, doubl
         if (i < NP) v = (type[i] != kPadType) ? 1.0 : 0.0;
     } else if (j < n1p) {
         v = (i == j) ? 1.0 : 0.0;
-    } else {   // j == n1p: right-hand side
+    } else if (j == n1p) {   // right-hand side
         if (i < NP) v = A[(long)NP + (long)i * ld];
         else if (i == NP) v = total_charge;
     }
@@ -118,10 +122,11 @@ __global__ void __launch_bounds__(1024) lu_panel_kernel(double* F, int n1p, int 
     }
 }
 
-// Row interchanges of one panel applied to the columns right of it (including the rhs column).
-__global__ void lu_swap_kernel(double* F, int n1p, int ncols, int k0, const int* ipiv) {
-    const int c = k0 + NB + blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncols) return;
+// Row interchanges of one panel applied to the columns [c_begin, c_end): those right of it (including the rhs column)
+// and the columns of the current outer block left of it (their L21 parts feed the delayed update in final row order).
+__global__ void lu_swap_kernel(double* F, int n1p, int c_begin, int c_end, int k0, const int* ipiv) {
+    const int c = c_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c_end) return;
     double* a = F + (long)c * n1p;
     for (int j = 0; j < NB; ++j) {
         const int r = k0 + j, p = ipiv[r];
@@ -133,16 +138,16 @@ __global__ void lu_swap_kernel(double* F, int n1p, int ncols, int k0, const int*
     }
 }
 
-// U12 = L11^-1 A12 (unit lower triangular 32 x 32), one thread per column.
-__global__ void __launch_bounds__(128) lu_trsm_kernel(double* F, int n1p, int ncols, int k0) {
+// U12 = L11^-1 A12 (unit lower triangular 32 x 32 at (k0, k0)) for the columns [c_begin, c_end), one thread per column.
+__global__ void __launch_bounds__(128) lu_trsm_kernel(double* F, int n1p, int c_begin, int c_end, int k0) {
     __shared__ double L[NB][NB + 1];
     for (int idx = threadIdx.x; idx < NB * NB; idx += blockDim.x) {
         const int i = idx % NB, j = idx / NB;
         L[i][j] = F[(long)(k0 + i) + (long)(k0 + j) * n1p];
     }
     __syncthreads();
-    const int c = k0 + NB + blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= ncols) return;
+    const int c = c_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= c_end) return;
     double* a = F + (long)c * n1p + k0;
     double x[NB];
 #pragma unroll
@@ -155,16 +160,19 @@ __global__ void __launch_bounds__(128) lu_trsm_kernel(double* F, int n1p, int nc
     for (int i = 0; i < NB; ++i) a[i] = x[i];
 }
 
-// A22 -= L21 U12, 64 x 64 tiles, K = 32, 4 x 4 outputs per thread.
-__global__ void __launch_bounds__(256) lu_gemm_kernel(double* F, int n1p, int ncols, int k0) {
+// A[r, c] -= L[r, k0 : k0 + 32] U[k0 : k0 + 32, c] for rows [r_begin, r_end) and columns [c_begin, c_end): 64 x 64
+// tiles, K = 32, 4 x 4 outputs per thread.
+__global__ void __launch_bounds__(256) lu_gemm_kernel(double* F, int n1p, int r_begin, int r_end, int c_begin, int c_end,
+                                                      int k0) {
     __shared__ double Ls[NB][64];
     __shared__ double Us[NB][64 + 1];
-    const int r0 = k0 + NB + blockIdx.x * 64, c0 = k0 + NB + blockIdx.y * 64;
+    const int r0 = r_begin + blockIdx.x * 64, c0 = c_begin + blockIdx.y * 64;
+    const int ncols = c_end;
     const int t = threadIdx.x;
     const long ld = n1p;
     for (int idx = t; idx < NB * 64; idx += 256) {
         const int r = idx & 63, j = idx >> 6;
-        Ls[j][r] = (r0 + r < n1p) ? F[(long)(r0 + r) + (long)(k0 + j) * ld] : 0.0;
+        Ls[j][r] = (r0 + r < r_end) ? F[(long)(r0 + r) + (long)(k0 + j) * ld] : 0.0;
     }
     for (int idx = t; idx < NB * 64; idx += 256) {
         const int j = idx & (NB - 1), c = idx / NB;
@@ -193,7 +201,7 @@ __global__ void __launch_bounds__(256) lu_gemm_kernel(double* F, int n1p, int nc
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             const int r = r0 + tr + a;
-            if (r < n1p) F[(long)r + (long)c * ld] -= acc[a][b];
+            if (r < r_end) F[(long)r + (long)c * ld] -= acc[a][b];
         }
     }
 }
@@ -232,6 +240,22 @@ __global__ void lu_back_update_kernel(double* F, int n1p, int kb) {
     rhs[i] -= s;
 }
 
+// Ut[c + k * right] = F[K0 + k, K1 + c]: the transposed copy of U12 (rows K0..K1 of the columns right of the outer
+// block) that gemm_nt_kernel takes as its B operand (n x K, column-major).
+__global__ void lu_transpose_kernel(const double* F, int n1p, int K0, int K1, int right, double* Ut) {
+    __shared__ double tile[32][33];
+    const int c0 = blockIdx.x * 32, kq = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int c = c0 + j, k = kq + threadIdx.x;          // coalesced along k (rows of F)
+        tile[j][threadIdx.x] = (c < right) ? F[(long)(K0 + k) + (long)(K1 + c) * n1p] : 0.0;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += 8) {
+        const int k = kq + j, c = c0 + threadIdx.x;          // coalesced along c
+        if (c < right) Ut[(long)c + (long)k * right] = tile[threadIdx.x][j];
+    }
+}
+
 // x (internal order, NP) and mu from the solved rhs column.
 __global__ void lu_extract_kernel(const double* F, int n1p, int NP, double* v, ScfState* state) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -242,33 +266,75 @@ __global__ void lu_extract_kernel(const double* F, int n1p, int NP, double* v, S
 
 }  // namespace
 
-int lu_padded_size(int NP) { return NP + 64; }
+int lu_padded_size(int NP) { return NP + kTile; }
+size_t lu_matrix_bytes(int NP) { return (size_t)(NP + kTile) * (NP + 2 * kTile) * 8; }
+size_t lu_workspace_bytes(int NP) { return (size_t)(NP + 2 * kTile) * OB * 8; }
 
-cudaError_t launch_lu_solve(const double* A, long ld, int NP, int nxp, int scf, double* F, const double* q,
+cudaError_t launch_lu_solve(const double* A, long ld, int NP, int nxp, int scf, double* F, double* Ut, const double* q,
                             const double* hard, const uint8_t* type, double total_charge, int* ipiv, double* v,
                             ScfState* state, unsigned long long* launches, cudaStream_t stream) {
     const int n1p = lu_padded_size(NP);
-    const int ncols = n1p + 1;
+    const int ncols = n1p + 1;          // matrix + right-hand side
+    const int ncolsP = n1p + kTile;     // ... padded to whole tiles
     {
-        dim3 grid(ncols, (n1p + 255) / 256);
+        dim3 grid(ncolsP, (n1p + 255) / 256);
         lu_build_kernel<<<grid, 256, 0, stream>>>(A, ld, NP, n1p, F, q, hard, type, nxp, scf, total_charge);
         ++*launches;
     }
-    for (int k0 = 0; k0 < n1p; k0 += NB) {
-        lu_panel_kernel<<<1, 1024, 0, stream>>>(F, n1p, k0, ipiv, &state[0].info);
-        const int right = ncols - (k0 + NB);
-        ++*launches;
-        if (right > 0) {
-            lu_swap_kernel<<<(right + 127) / 128, 128, 0, stream>>>(F, n1p, ncols, k0, ipiv);
-            lu_trsm_kernel<<<(right + 127) / 128, 128, 0, stream>>>(F, n1p, ncols, k0);
-            *launches += 2;
-            const int below = n1p - (k0 + NB);
-            if (below > 0) {
-                dim3 grid((below + 63) / 64, (right + 63) / 64);
-                lu_gemm_kernel<<<grid, 256, 0, stream>>>(F, n1p, ncols, k0);
+    for (int K0 = 0; K0 < n1p; K0 += OB) {
+        const int K1 = K0 + OB;         // n1p is a multiple of 128: whole outer blocks
+        for (int k0 = K0; k0 < K1; k0 += NB) {
+            lu_panel_kernel<<<1, 1024, 0, stream>>>(F, n1p, k0, ipiv, &state[0].info);
+            ++*launches;
+            // interchanges: everything right of the panel, and the outer block's columns left of it
+            lu_swap_kernel<<<(ncols - (k0 + NB) + 127) / 128, 128, 0, stream>>>(F, n1p, k0 + NB, ncols, k0, ipiv);
+            ++*launches;
+            if (k0 > K0) {
+                lu_swap_kernel<<<(k0 - K0 + 127) / 128, 128, 0, stream>>>(F, n1p, K0, k0, k0, ipiv);
+                ++*launches;
+            }
+            // eager update of the rest of the outer block
+            const int inner = K1 - (k0 + NB);
+            if (inner > 0) {
+                lu_trsm_kernel<<<(inner + 127) / 128, 128, 0, stream>>>(F, n1p, k0 + NB, K1, k0);
+                dim3 grid((n1p - (k0 + NB) + 63) / 64, (inner + 63) / 64);
+                lu_gemm_kernel<<<grid, 256, 0, stream>>>(F, n1p, k0 + NB, n1p, k0 + NB, K1, k0);
+                *launches += 2;
+            }
+        }
+        // delayed update of everything right of the outer block: U12 = L11^-1 A12 by 32-row blocks, then
+        // A22 -= L21 U12 with K = 128 on the tensor cores (B operand = U12^T, copied out)
+        const int right = ncolsP - K1;
+        if (right <= 0) continue;
+        for (int jb = 0; jb < OB / NB; ++jb) {
+            const int kk = K0 + jb * NB;
+            lu_trsm_kernel<<<(ncols - K1 + 127) / 128, 128, 0, stream>>>(F, n1p, K1, ncols, kk);
+            ++*launches;
+            if (jb + 1 < OB / NB) {
+                dim3 grid((K1 - (kk + NB) + 63) / 64, (ncols - K1 + 63) / 64);
+                lu_gemm_kernel<<<grid, 256, 0, stream>>>(F, n1p, kk + NB, K1, K1, ncols, kk);
                 ++*launches;
             }
         }
+        const int below = n1p - K1;
+        if (below <= 0) continue;
+        {
+            dim3 grid((right + 31) / 32, OB / 32);
+            lu_transpose_kernel<<<grid, dim3(32, 8), 0, stream>>>(F, n1p, K0, K1, right, Ut);
+            ++*launches;
+        }
+        GemmArgs g{};
+        g.A = F + (long)K1 + (long)K0 * n1p;
+        g.lda = n1p;
+        g.B = Ut;
+        g.ldb = right;
+        g.C = F + (long)K1 + (long)K1 * n1p;
+        g.ldc = n1p;
+        g.K = OB;
+        g.subtract = 1;
+        cudaError_t e = launch_gemm_nt(g, below / kTile, right / kTile, 1, stream);
+        if (e != cudaSuccess) return e;
+        ++*launches;
     }
     for (int kb = n1p / NB - 1; kb >= 0; --kb) {
         lu_back_diag_kernel<<<1, NB, 0, stream>>>(F, n1p, kb);

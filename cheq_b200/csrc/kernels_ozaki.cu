@@ -262,16 +262,20 @@ __global__ void __launch_bounds__(128) oz_rowmax_kernel(const double* __restrict
     const long rsrc = (tile_list ? (long)tile_list[blockIdx.x] : (long)blockIdx.x) * 128 + threadIdx.x;
     const int k0 = blockIdx.y * kchunk, k1 = min(K, k0 + kchunk);
     const double* p = X + rsrc + (long)k0 * ld;
-    double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
+    // 16 independent loads in flight per thread: the launches are short (K = 512 ... 8192 in chunks of 128 columns)
+    // and latency-bound otherwise
+    double mm[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) mm[u] = 0.0;
     int k = k0;
-    for (; k + 4 <= k1; k += 4, p += 4 * ld) {
-        m0 = fmax(m0, fabs(p[0]));
-        m1 = fmax(m1, fabs(p[ld]));
-        m2 = fmax(m2, fabs(p[2 * ld]));
-        m3 = fmax(m3, fabs(p[3 * ld]));
+    for (; k + 16 <= k1; k += 16, p += 16 * ld) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) mm[u] = fmax(mm[u], fabs(p[(long)u * ld]));
     }
-    for (; k < k1; ++k, p += ld) m0 = fmax(m0, fabs(p[0]));
-    m0 = fmax(fmax(m0, m1), fmax(m2, m3));
+    for (; k < k1; ++k, p += ld) mm[0] = fmax(mm[0], fabs(p[0]));
+#pragma unroll
+    for (int u = 1; u < 16; ++u) mm[0] = fmax(mm[0], mm[u]);
+    const double m0 = mm[0];
     atomicMax(mx + r, (unsigned long long)__double_as_longlong(m0));
 }
 

@@ -292,6 +292,26 @@ def test_pivoted_lu_fallback_on_vanishing_pivot(gpu_ctx, oracle):
     assert_parity(res, oracle.solve(Z, xyz, 0.0, oracle_opts(oracle, o)))
 
 
+@pytest.mark.parametrize("waters,scf", [(40, True), (333, True), (333, False)])
+def test_pivoted_lu_path_forced(oracle, waters, scf):
+    """The pivoted-LU path (the reference's own algorithm, implementation.rs:574-576) forced on ordinary systems
+    (CHEQ_FORCE_LU=1): 32-column panels with partial pivoting inside 128-column outer blocks, the update right of an
+    outer block on the FP64 tensor cores.  999 atoms = 9 outer blocks."""
+    import os
+    Z, xyz = workloads.water_cluster(waters)
+    o = SolverOptions(hydrogen_scf=scf)
+    ref = oracle.solve(Z, xyz, 0.0, oracle_opts(oracle, o))
+    os.environ["CHEQ_FORCE_LU"] = "1"
+    try:
+        ctx = cheq_b200.Context(0)
+    finally:
+        del os.environ["CHEQ_FORCE_LU"]
+    res = QEqSolver(get_default_parameters(), o, ctx).solve(atoms_of(Z, xyz), 0.0)
+    assert ctx.stats()["lu_fallback_frames"] == 1
+    assert_parity(res, ref)
+    ctx.close()
+
+
 # ---- the reference's solver unit tests (implementation.rs:620-1013) -------------------------------------------
 def test_reference_solver_unit_tests(gpu_ctx):
     s = solver(gpu_ctx)
