@@ -88,13 +88,14 @@ __device__ __forceinline__ bool oz_try_wait(uint32_t bar, uint32_t parity) {
     return ok != 0;
 }
 
-// bounded wait: false = gave up (another role died or ~1 s passed); *dead and *error are raised once
+// bounded wait: false = gave up (another role died or ~8 s of SM clock passed -- long enough to survive time-slicing with
+// another process on the same GPU); *dead and *error are raised once
 __device__ __forceinline__ bool oz_wait(uint32_t bar, uint32_t parity, volatile int* dead, int* error, int code) {
     if (oz_try_wait(bar, parity)) return true;
     const long long t0 = clock64();
     while (!oz_try_wait(bar, parity)) {
         if (*dead) return false;
-        if (clock64() - t0 > 2000000000ll) {
+        if (clock64() - t0 > 16000000000ll) {
             *dead = 1;
             atomicCAS(error, 0, code);
             return false;

@@ -256,3 +256,18 @@ def test_s100k_generator_is_seeded_and_physical():
     assert Z[400:403] == [8, 1, 1] and set(Z[:400]) <= {1, 6, 7, 8}
     d, _ = cKDTree(xyz).query(xyz, k=2)
     assert d[:, 1].min() > 0.9                      # minimum inter-atomic distance
+
+
+# ---- schedule of the pivoted-LU fallback (kernels_lu.cu) -----------------------------------------------------------
+def test_two_level_lu_schedule_model():
+    """tests/lu_model.py restates launch_lu_solve's kernel sequence; on a symmetric indefinite matrix that needs
+    pivoting in (nearly) every column it must agree with LAPACK."""
+    import lu_model
+    rng = np.random.default_rng(7)
+    for n in (128, 384):
+        A = rng.normal(size=(n, n))
+        A = A + A.T
+        A[0, 0] = 0.0                      # a vanishing leading pivot, the case the fallback exists for
+        b = rng.normal(size=n)
+        x = lu_model.solve(A, b)
+        assert np.max(np.abs(x - np.linalg.solve(A, b))) < 1e-10
