@@ -268,19 +268,28 @@ __global__ void __launch_bounds__(128) oz_rowmax_kernel(const double* __restrict
     double mm[16];
 #pragma unroll
     for (int u = 0; u < 16; ++u) mm[u] = 0.0;
+    bool finite = true;   // fmax drops NaN: track it, so that a NaN / Inf entry poisons its row like it would in fp64
     int k = k0;
     for (; k + 16 <= k1; k += 16, p += 16 * ld) {
 #pragma unroll
-        for (int u = 0; u < 16; ++u) mm[u] = fmax(mm[u], fabs(p[(long)u * ld]));
+        for (int u = 0; u < 16; ++u) {
+            const double ax = fabs(p[(long)u * ld]);
+            finite = finite && (ax < INFINITY);
+            mm[u] = fmax(mm[u], ax);
+        }
     }
-    for (; k < k1; ++k, p += ld) mm[0] = fmax(mm[0], fabs(p[0]));
+    for (; k < k1; ++k, p += ld) {
+        const double ax = fabs(p[0]);
+        finite = finite && (ax < INFINITY);
+        mm[0] = fmax(mm[0], ax);
+    }
 #pragma unroll
     for (int u = 1; u < 16; ++u) mm[0] = fmax(mm[0], mm[u]);
-    const double m0 = mm[0];
+    const double m0 = finite ? mm[0] : INFINITY;
     atomicMax(mx + r, (unsigned long long)__double_as_longlong(m0));
 }
 
-// exponent e with rowmax < 2^e (0 for an all-zero row)
+// exponent e with rowmax < 2^e (0 for an all-zero row; 1025 marks a row with a NaN / Inf entry)
 __device__ __forceinline__ int oz_exponent(unsigned long long bits) {
     const int E = (int)((bits >> 52) & 0x7ff);
     if (bits == 0ull) return 0;
@@ -314,7 +323,8 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
         const long row = (long)rb * RB + r;   // row of the sliced operand; its source row in X differs in list mode
         const long rsrc = tile_list ? (long)tile_list[row >> 7] * 128 + (row & 127) : row;
         const int e = oz_exponent(mx[row]);
-        if (kt == 0 && c16 == 0) scale_out[row] = ldexp(1.0, e - 6);
+        // a row with a non-finite entry gets a NaN scale: every entry of C it touches becomes NaN, as in the fp64 path
+        if (kt == 0 && c16 == 0) scale_out[row] = (e == 1025) ? __longlong_as_double(0x7ff8000000000000ll) : ldexp(1.0, e - 6);
         const double sc = ldexp(1.0, B - e);
         const double* src = X + rsrc + ((long)kt * 128 + c16 * 16) * ld;
         long long v[16];

@@ -12,7 +12,6 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
-#include <functional>
 #include <random>
 #include <vector>
 
@@ -47,21 +46,22 @@ static double run_case(const Case& c, int* d_err) {
     };
     auto uni = [&]() { return (double)(next() >> 11) * (2.0 / 9007199254740992.0) - 1.0; };
     auto wide = [&]() { const unsigned long long z = next(); return std::ldexp((double)(z >> 11) * (2.0 / 9007199254740992.0) - 1.0, -(int)(z & 7)); };
-    struct { std::function<double()> f; double operator()(std::mt19937_64&) { return f(); } } nd{uni};
     std::vector<double> A((size_t)lda * K), B((size_t)ldb * K), C((size_t)ldc * n), C0;
     std::vector<double> rs(m), cs(n);
-    for (auto& v : rs) v = std::exp(2.0 * nd(rng));
-    for (auto& v : cs) v = std::exp(2.0 * nd(rng));
+    for (auto& v : rs) v = std::exp(2.0 * uni());
+    for (auto& v : cs) v = std::exp(2.0 * uni());
     for (long k = 0; k < K; ++k) {
         for (long i = 0; i < lda; ++i) A[i + k * lda] = i < m ? rs[i] * wide() : 1e300;
         for (long i = 0; i < ldb; ++i) B[i + k * ldb] = i < n ? cs[i] * uni() : 1e300;
     }
-    if (m >= 256)   // an all-zero row and a row with one huge entry
+    if (m >= 256) {  // an all-zero row, a row with one huge entry, and a row with one NaN (must poison its row of C only)
         for (long k = 0; k < K; ++k) {
             A[5 + k * lda] = 0.0;
             if (k == 3) A[6 + k * lda] = 1e12;
         }
-    for (auto& v : C) v = nd(rng);
+        A[7 + 9 * lda] = std::nan("");
+    }
+    for (auto& v : C) v = uni();
     C0 = C;
     std::vector<int> neg_cnt(K / 128, 0), neg_idx(K, 0);
     std::vector<double> sgn(K, 1.0);
@@ -115,12 +115,17 @@ static double run_case(const Case& c, int* d_err) {
         if (s < 8) { i = (s & 1) ? m - 1 - s : s; j = (s & 2) ? n - 1 - s : s; }
         if (s == 8 && m >= 256) { i = 5; }
         if (s == 9 && m >= 256) { i = 6; }
+        if (s == 10 && m >= 256) { i = 7; }
         long double ref = 0.0L;
         for (long k = 0; k < K; ++k) ref += (long double)A[i + k * lda] * (long double)(sgn[k] * B[j + k * ldb]);
         const double c0 = C0[i + j * ldc], got = C[i + j * ldc];
         const bool skipped = c.lower && (i / 128) * 128 + 127 < (j / 64) * 64;
         if (skipped) {
             worst_untouched = std::max(worst_untouched, std::fabs(got - c0));
+            continue;
+        }
+        if (m >= 256 && i == 7) {   // the NaN row
+            if (!std::isnan(got)) { worst = 1.0; bad_i = i; bad_j = j; }
             continue;
         }
         const long double want = c.subtract ? (long double)c0 - ref : ref;
