@@ -85,3 +85,33 @@ def test_round2_s100k_line_is_a_bench_py_line():
     d = _line("r2_bench_s100k_8gpu_v1.json")
     assert d["metric"] == "qeq_solve_time_n100k_sto_fp64" and d["n_gpus"] == 8 and "S100k" in d["config"]["workload"]
     assert d["config"]["factor_tflops_overall"] / d["roofline"]["peak"] >= 0.5   # north_star: >= 50 % of FP64 peak
+
+
+# ---- round 2, tcgen05 slice-product updates ------------------------------------------------------------------------
+def test_tcgen05_line_reports_the_new_dominant_kernel_against_the_int8_peak():
+    d = _line("r2_bench_v5_final.json")
+    assert BASE_KEYS <= set(d), BASE_KEYS - set(d)
+    assert d["metric"] == "qeq_solve_time_n20k_sto_fp64" and d["n_gpus"] == 1 and d["warmup"] >= 3
+    assert d["value"] < 0.2 and d["e2e"]["value"] < 0.2          # was 0.299 s with FP64 DMMA only, 0.767 s in round 1
+    p = d["parity"]
+    assert p["ok"] and p["iterations"] == p["iterations_ref"] == 18 and p["dq"] <= 1e-8 and p["dmu"] <= 1e-8
+    assert p["max_delta_trace_diff"] <= 1e-9
+    r = d["roofline"]
+    assert "tcgen05" in r["kernel"] and r["bound"] == "tensor" and r["unit"] == "TFLOP/s"
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and 0.3 < r["frac"] < 1.0
+    assert r["peak"] >= 2 * 1500                                  # int8 dense tensor peak: at least 2 x the bf16 figure
+    assert r["fp64_equivalent_tflops"] > 2 * 35.4                 # more than twice what any FP64 GEMM can do on this part
+    assert r["traffic"] and r["largest_launch"]["tensor_pipe_active"] > 0.8
+    o = d["roofline_other_gemm"]
+    assert "DMMA" in o["kernel"] and 0 < o["frac"] < 1
+    assert d["e2e"]["clocks"]["reasons"] == [] and d["clocks"]["reasons"] == []
+
+
+@pytest.mark.parametrize("name, gpus", [("r2_bench_dist2_v2_tcgen05.json", 2), ("r2_bench_dist8_v3_tcgen05.json", 8)])
+def test_tcgen05_multi_gpu_lines(name, gpus):
+    d = _line(name)
+    assert d["n_gpus"] == gpus and d["scaling"] == "strong"
+    chk = d["dist_check"]
+    assert chk["dq"] < 1e-10 and chk["dmu"] < 1e-10 and chk["iterations"][0] == chk["iterations"][1]
+    assert d["value"] < _line("r2_bench_v5_final.json")["value"]              # faster than one GPU ...
+    assert d["value"] < _line({2: "r2_bench_dist2_v1.json", 8: "r2_bench_dist8_v1.json"}[gpus])["value"]   # ... and than DMMA
